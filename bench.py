@@ -1,0 +1,297 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: batched rodent env steps/s (BASELINE.json metric, configs[1]).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+b200 arm: `rodent_0.xml`, 4096 envs per GPU, random actions U(-1,1) redrawn every control step (pre-generated,
+resident in HBM), one "step" = Rodent.step for the whole batch = 10 physics substeps + reward / done / obs +
+the fused Brax episode / auto-reset wrappers.  Timed with CUDA events around every step on the launching
+stream, L2 flushed between steps (outside the events), max over ranks.  `e2e` is the same step through
+rr_env_step_host with pinned HOST action / obs / reward / done buffers (copies inside the timed region).
+reference arm: the CPU oracle (oracle/, a C restatement of the MJX step -- mujoco / mjx / brax are not
+installable in this image) on all host cores, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ENVS_PER_GPU = 4096
+N_FRAMES = 10
+ALGO_BYTES_PER_ENV_STEP = 7204  # state in/out + action + 1263-float obs + scalars
+FP32_PEAK_TFLOPS_NOMINAL = 148 * 128 * 2 * 1.965e9 / 1e12  # 74.4, no measured FP32 peak in MEASURED_PEAKS.json
+
+
+def synthetic_track(n=250):
+    return np.stack([0.002 * np.arange(n), np.zeros(n), np.full(n, 0.055)], 1).astype(np.float32)
+
+
+# ------------------------------------------------------------------------------------------------ CPU oracle arm
+def _oracle_worker(args):
+    seed, n_steps, iterations, ls_iterations = args
+    from brax_rodent_run_b200 import mjcf, model_blob
+    from oracle import oracle
+    m = mjcf.FlatModel.load(os.path.join(ROOT, "brax_rodent_run_b200", "assets", "rodent_0.npz"))
+    blob = model_blob.pack(m)
+    env = oracle.OracleRodentEnv(blob, (m.nq, m.nv, m.nu, m.nbody), synthetic_track(), iterations=iterations,
+                                 ls_iterations=ls_iterations, precision="f32")
+    rng = np.random.default_rng(seed)
+    q = m.qpos0.copy()
+    sf = int(rng.integers(0, 100))
+    q[:3] = synthetic_track()[sf]
+    env.reset(sf, q + rng.uniform(-.01, .01, m.nq), rng.uniform(-.01, .01, m.nv))
+    t0 = time.perf_counter()
+    for _ in range(n_steps):
+        env.step(rng.uniform(-1, 1, m.nu))
+    return time.perf_counter() - t0
+
+
+def cpu_oracle_rate(n_steps, iterations, ls_iterations, cores=None):
+    """env-steps/s of the oracle with one environment per host core."""
+    from oracle import oracle
+    oracle.build()
+    cores = cores or os.cpu_count() or 1
+    with mp.get_context("spawn").Pool(cores) as pool:
+        t0 = time.perf_counter()
+        pool.map(_oracle_worker, [(s, n_steps, iterations, ls_iterations) for s in range(cores)])
+        wall = time.perf_counter() - t0
+    return cores * n_steps / wall, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = 40  # env steps per core per bench "step": bounded sample of the 4096-env workload
+    for _ in range(min(args.warmup, 1)):
+        cpu_oracle_rate(5, args.iterations, args.ls_iterations)
+    rates, t0 = [], time.perf_counter()
+    for _ in range(args.steps):
+        r, cores = cpu_oracle_rate(n, args.iterations, args.ls_iterations)
+        rates.append(r)
+    wall = time.perf_counter() - t0
+    value = float(np.mean(rates))
+    sample = f"{cores} envs (one per core) x {n} env steps per bench step, rodent_0.xml, oracle fp32 C port of the MJX step"
+    print(json.dumps({
+        "impl": "reference", "metric": "rodent env-steps/s", "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "mujoco / mujoco-mjx / brax / jax are absent from this image (no wheels, no network): the reference arm "
+                "is the repo's C restatement of the MJX step (oracle/rr_oracle.c) on all host cores",
+    }))
+
+
+def workload_config(args):
+    return {"workload": "rodent_0.xml run task, Rodent.step (10 substeps of 2 ms, CG solver) with random actions, "
+                        f"{ENVS_PER_GPU} envs/GPU", "envs_per_gpu": ENVS_PER_GPU, "n_frames": N_FRAMES, "solver": "cg",
+            "iterations": args.iterations, "ls_iterations": args.ls_iterations, "episode_length": 1000,
+            "terminate_when_unhealthy": True, "l2": "flushed between timed steps (256 MiB write outside the event pair)",
+            "includes": "physics + reward/done/metrics + 1263-float obs + fused Episode/AutoReset wrappers"}
+
+
+# ------------------------------------------------------------------------------------------------ clocks sampler
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for k, nme in enumerate(names):
+                    if r[3 + k].lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ B200 arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from brax_rodent_run_b200 import _lib
+    from brax_rodent_run_b200.env import Rodent
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the b200 arm has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    B, K, W = ENVS_PER_GPU, args.steps, args.warmup
+    env = Rodent(synthetic_track(), num_envs=B, device=dev, model="rodent_0", solver="cg", iterations=args.iterations,
+                 ls_iterations=args.ls_iterations, terminate_when_unhealthy=True, kinematics_outputs=False)
+    env.wrap_for_training(episode_length=1000)
+    L = env._L
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    state = env.reset(gen)
+    actions = torch.rand((K + W, B, env.action_size), generator=gen, device=dev) * 2 - 1  # resident in HBM
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for i in range(W):
+        state = env.step(state, actions[i])
+    barrier()
+
+    # ---- device-resident timing: per-step event pairs, L2 flushed in between -------------------------------
+    sampler = ClockSampler(local) if rank == 0 else None
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    launches0 = L.rr_launch_count()
+    barrier()
+    t_wall0 = time.perf_counter()
+    for i in range(K):
+        flush.fill_(float(i))
+        ev[i][0].record()
+        state = env.step(state, actions[W + i])
+        ev[i][1].record()
+    barrier()
+    wall = time.perf_counter() - t_wall0
+    launches = L.rr_launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+    ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = float(sum(ms))
+    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    value = world * B * K / (total_ms * 1e-3)
+    done_frac = float(state.done.mean().item())
+
+    # ---- end to end through the host-buffer C-ABI call -----------------------------------------------------------
+    Ke = min(K, 50)
+    h_act = torch.empty((B, env.action_size), pin_memory=True)
+    h_obs = torch.empty((B, env.observation_size), pin_memory=True)
+    h_rew = torch.empty((B,), pin_memory=True)
+    h_done = torch.empty((B,), pin_memory=True)
+    host_actions = (torch.rand((Ke + 2, B, env.action_size)) * 2 - 1)
+    buf, tens = env._out_buffers()
+    ps = state.pipeline_state
+    for k_, v_ in (("qpos", ps.qpos), ("qvel", ps.qvel), ("act", ps.act), ("qacc_warmstart", ps.qacc_warmstart), ("time", ps.time),
+                   ("cur_frame", state.info["cur_frame"]), ("done", state.done), ("steps", state.info["steps"])):
+        tens[k_].copy_(v_)
+    f = state.info["first_pipeline_state"]
+    buf.first_qpos, buf.first_qvel, buf.first_act = f.qpos.data_ptr(), f.qvel.data_ptr(), f.act.data_ptr()
+    buf.first_qacc_warmstart, buf.first_time, buf.first_obs = f.qacc_warmstart.data_ptr(), f.time.data_ptr(), state.info["first_obs"].data_ptr()
+    stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+    def host_step(i):
+        h_act.copy_(host_actions[i])
+        _lib.check(L, L.rr_env_step_host(env._env, ctypes.byref(buf), ctypes.c_void_p(h_act.data_ptr()), N_FRAMES,
+                                         ctypes.c_void_p(h_obs.data_ptr()), ctypes.c_void_p(h_rew.data_ptr()),
+                                         ctypes.c_void_p(h_done.data_ptr()), stream))
+
+    host_step(0); host_step(1)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(Ke):
+        host_step(2 + i)
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * Ke / float(t.item())
+    h2d = B * env.action_size * 4
+    d2h = B * (env.observation_size + 2) * 4
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak_gbs, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)") if "hbm_gbs" in peaks else (6650.0, "fallback")
+        kernel_ms = total_ms / K  # one rr_step_kernel launch per step; the event pair brackets only that launch
+        achieved_gbs = ALGO_BYTES_PER_ENV_STEP * B / (kernel_ms * 1e-3) / 1e9
+        flops_per_env_step = 10 * (182e3 + args.iterations * (22962 + 1421 * (2 + 3 * args.ls_iterations)))
+        achieved_tflops = flops_per_env_step * B / (kernel_ms * 1e-3) / 1e12
+        out = {
+            "metric": "rodent env-steps/s", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(args),
+            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": peak_gbs, "unit": "GB/s", "frac": achieved_gbs / peak_gbs,
+                         "traffic": None, "peak_source": peak_src, "kernel": "rr_step_kernel<3>",
+                         "note": "the kernel is FP32-issue/latency bound, not HBM bound (SURVEY 8d); see roofline_fp32"},
+            "roofline_fp32": {"achieved": achieved_tflops, "peak": FP32_PEAK_TFLOPS_NOMINAL, "unit": "TFLOP/s",
+                              "frac": achieved_tflops / FP32_PEAK_TFLOPS_NOMINAL, "peak_source": "nominal 148 SM x 128 lanes x 2 x 1.965 GHz",
+                              "flops_per_env_step": flops_per_env_step, "flops_source": "SURVEY 8(d) dense-row operation-count estimate (upper bound: the kernel skips inactive rows)"},
+            "wall_s": wall, "done_frac_last_step": done_frac,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            rate, cores = cpu_oracle_rate(20, args.iterations, args.ls_iterations)
+            out["cpu_baseline"] = {"value": rate, "unit": "env-steps/s", "cores": cores, "kind": "port",
+                                   "sample": f"{cores} envs (one per core) x 20 env steps, rodent_0.xml, oracle fp32"}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--iterations", type=int, default=8)      # brax_rodent_run_ppo.py:52
+    ap.add_argument("--ls-iterations", type=int, default=8)   # brax_rodent_run_ppo.py:53
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,285 @@
+/* rr_api_impl.inl -- body of the C ABI declared in include/rr_b200.h.
+ *
+ * Included once by rr_api.cu (the product: CUDA backend) and once by tests/emu/rr_emu.cpp (test-only host
+ * backend that runs the same kernel text with the 32 lanes as fibers).  The including file provides:
+ *   int  rrb_set_device(int device);
+ *   int  rrb_malloc(void **p, size_t bytes);   void rrb_free(void *p);
+ *   int  rrb_h2d(void *dst, const void *src, size_t bytes, void *stream);
+ *   int  rrb_d2h(void *dst, const void *src, size_t bytes, void *stream);
+ *   int  rrb_sync(void *stream);
+ *   int  rrb_launch_step(const RRModelDev &m, const RRStepArgs &a, void *stream);
+ *   int  rrb_launch_gae(...);
+ *   const char *rrb_error();
+ */
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../include/rr_b200.h"
+#include "rr_model_build.h"
+
+static thread_local std::string g_rr_error;
+static std::atomic<long long> g_rr_launches{0};
+
+struct rr_model {
+  RRHostModel host;
+  RRModelDev dev;  /* pointers bound to device copies */
+  int32_t *d_ibuf;
+  float *d_fbuf;
+};
+
+struct rr_env {
+  const rr_model *model;
+  int B, device;
+  RRTask task;
+  float *d_track;
+  int episode_length;
+  float *d_dbg;
+  long long *d_prof;
+  float *d_action_stage; /* [B, nu] staging for the host-buffer entry point */
+};
+
+static int rr_fail(int code, const std::string &msg) {
+  g_rr_error = msg;
+  return code;
+}
+
+extern "C" const char *rr_last_error(void) { return g_rr_error.c_str(); }
+extern "C" long long rr_launch_count(void) { return g_rr_launches.load(); }
+
+extern "C" int rr_model_create(const int32_t *dir, int32_t ndir, const int32_t *idata, int32_t ni, const double *fdata,
+                               int32_t nf, rr_model **out) {
+  if (!dir || !idata || !fdata || !out) return rr_fail(RR_EINVAL, "rr_model_create: null argument");
+  if (ndir != 2 * RR_NFIELDS) return rr_fail(RR_EINVAL, "rr_model_create: blob directory does not match rr_model_fields.h");
+  for (int k = 0; k < RR_NFIELDS; k++)
+    if (dir[2 * k] < 0 || dir[2 * k + 1] < 0) return rr_fail(RR_EINVAL, "rr_model_create: negative offset in blob directory");
+  rr_model *m = new rr_model();
+  m->d_ibuf = nullptr;
+  m->d_fbuf = nullptr;
+  try {
+    rr_host_model_build(m->host, dir, idata, ni, fdata, nf);
+  } catch (const std::exception &ex) {
+    std::string msg = ex.what();
+    delete m;
+    return rr_fail(msg.rfind("NotImplemented", 0) == 0 ? RR_ENOTIMPL : RR_EINVAL, msg);
+  }
+  m->dev = m->host.dev;
+  *out = m;
+  return RR_OK;
+}
+
+extern "C" void rr_model_destroy(rr_model *m) {
+  if (!m) return;
+  if (m->d_ibuf) rrb_free(m->d_ibuf);
+  if (m->d_fbuf) rrb_free(m->d_fbuf);
+  delete m;
+}
+
+extern "C" int rr_model_set_solver(rr_model *m, int32_t solver, int32_t iterations, int32_t ls_iterations) {
+  if (!m) return rr_fail(RR_EINVAL, "rr_model_set_solver: null model");
+  if (solver != 0) return rr_fail(RR_ENOTIMPL, "NotImplemented: only the CG solver is available on the device path");
+  if (iterations < 1 || ls_iterations < 0) return rr_fail(RR_EINVAL, "rr_model_set_solver: bad iteration counts");
+  m->dev.solver = m->host.dev.solver = solver;
+  m->dev.iterations = m->host.dev.iterations = iterations;
+  m->dev.ls_iterations = m->host.dev.ls_iterations = ls_iterations;
+  return RR_OK;
+}
+
+static int rr_debug_stride_of(const RRModelDev &d) {
+  int n = 0;
+  for (int f = 0; f < rr::RR_DBG_NFIELDS; f++) n += rr::dbg_count(d, f);
+  return n;
+}
+
+extern "C" int rr_model_dims(const rr_model *m, rr_dims *o) {
+  if (!m || !o) return rr_fail(RR_EINVAL, "rr_model_dims: null argument");
+  const RRModelDev &d = m->dev;
+  o->nq = d.nq; o->nv = d.nv; o->nu = d.nu; o->na = d.na; o->nbody = d.nbody; o->njnt = d.njnt; o->ngeom = d.ngeom;
+  o->ncon = d.ncon; o->nlimit = d.nlimit; o->nefc = d.nefc; o->nM = d.nM; o->nroot = d.nroot;
+  o->obs_dim = m->host.obs_dim;
+  o->smem_bytes = d.sm.total * (int)sizeof(float);
+  o->debug_stride = rr_debug_stride_of(d);
+  o->timestep = d.timestep;
+  return RR_OK;
+}
+
+static const char *const kDbgNames[rr::RR_DBG_NFIELDS] = {
+    "xpos", "xquat", "subtree_com", "cinert", "cdof", "cvel", "qM_sparse", "qLD_sparse", "qfrc_bias", "qfrc_passive",
+    "qfrc_actuator", "qfrc_smooth", "qacc_smooth", "contact_dist", "contact_pos", "contact_frame", "efc_J", "efc_D",
+    "efc_aref", "efc_force", "qacc", "qfrc_constraint", "scalars"};
+
+extern "C" int rr_debug_field(const rr_model *m, const char *name, int32_t *offset, int32_t *count) {
+  if (!m || !name) return rr_fail(RR_EINVAL, "rr_debug_field: null argument");
+  for (int f = 0; f < rr::RR_DBG_NFIELDS; f++)
+    if (!std::strcmp(name, kDbgNames[f])) {
+      if (offset) *offset = rr::dbg_offset(m->dev, f);
+      if (count) *count = rr::dbg_count(m->dev, f);
+      return RR_OK;
+    }
+  return rr_fail(RR_EINVAL, std::string("rr_debug_field: unknown field ") + name);
+}
+
+static const char *const kProfNames[RR_NPROF] = {"load", "kinematics", "com_pos", "crb", "mass_matrix", "factor", "com_vel",
+                                                  "rne", "smooth", "collision", "make_constraint", "solver_init",
+                                                  "solver_linesearch", "solver_update", "euler", "epilogue"};
+extern "C" int rr_prof_count(void) { return RR_NPROF; }
+extern "C" const char *rr_prof_name(int32_t i) { return (i >= 0 && i < RR_NPROF) ? kProfNames[i] : ""; }
+
+extern "C" int rr_env_create(const rr_model *cm, int32_t num_envs, int32_t device, rr_env **out) {
+  if (!cm || !out || num_envs < 1) return rr_fail(RR_EINVAL, "rr_env_create: bad argument");
+  rr_model *m = const_cast<rr_model *>(cm);
+  if (rrb_set_device(device)) return rr_fail(RR_ECUDA, rrb_error());
+  if (!m->d_ibuf) { /* first use: upload the tables */
+    if (rrb_malloc((void **)&m->d_ibuf, m->host.ibuf.size() * sizeof(int32_t)) ||
+        rrb_malloc((void **)&m->d_fbuf, m->host.fbuf.size() * sizeof(float)) ||
+        rrb_h2d(m->d_ibuf, m->host.ibuf.data(), m->host.ibuf.size() * sizeof(int32_t), nullptr) ||
+        rrb_h2d(m->d_fbuf, m->host.fbuf.data(), m->host.fbuf.size() * sizeof(float), nullptr) || rrb_sync(nullptr))
+      return rr_fail(RR_ECUDA, rrb_error());
+    rr_host_model_bind(m->host, m->dev, m->d_ibuf, m->d_fbuf);
+  }
+  rr_env *e = new rr_env();
+  std::memset(e, 0, sizeof(*e));
+  e->model = m;
+  e->B = num_envs;
+  e->device = device;
+  e->task.ctrl_cost_weight = 0.1f;
+  e->task.healthy_reward = 1.0f;
+  e->task.healthy_z_lo = 0.03f;
+  e->task.healthy_z_hi = 0.5f;
+  e->task.terminate_when_unhealthy = 1;
+  if (rrb_malloc((void **)&e->d_action_stage, (size_t)num_envs * (m->dev.nu > 0 ? m->dev.nu : 1) * sizeof(float))) {
+    delete e;
+    return rr_fail(RR_ECUDA, rrb_error());
+  }
+  *out = e;
+  return RR_OK;
+}
+
+extern "C" void rr_env_destroy(rr_env *e) {
+  if (!e) return;
+  if (e->d_track) rrb_free(e->d_track);
+  if (e->d_action_stage) rrb_free(e->d_action_stage);
+  delete e;
+}
+
+extern "C" int rr_env_set_task(rr_env *e, const float *track_pos, int32_t track_len, float ctrl_cost_weight,
+                               float healthy_reward, float healthy_z_lo, float healthy_z_hi, int32_t terminate_when_unhealthy) {
+  if (!e || !track_pos || track_len < 1) return rr_fail(RR_EINVAL, "rr_env_set_task: bad argument");
+  if (rrb_set_device(e->device)) return rr_fail(RR_ECUDA, rrb_error());
+  if (e->d_track) rrb_free(e->d_track);
+  e->d_track = nullptr;
+  if (rrb_malloc((void **)&e->d_track, (size_t)track_len * 3 * sizeof(float)) ||
+      rrb_h2d(e->d_track, track_pos, (size_t)track_len * 3 * sizeof(float), nullptr) || rrb_sync(nullptr))
+    return rr_fail(RR_ECUDA, rrb_error());
+  e->task.track_pos = e->d_track;
+  e->task.track_len = track_len;
+  e->task.ctrl_cost_weight = ctrl_cost_weight;
+  e->task.healthy_reward = healthy_reward;
+  e->task.healthy_z_lo = healthy_z_lo;
+  e->task.healthy_z_hi = healthy_z_hi;
+  e->task.terminate_when_unhealthy = terminate_when_unhealthy ? 1 : 0;
+  return RR_OK;
+}
+
+extern "C" int rr_env_set_wrappers(rr_env *e, int32_t episode_length) {
+  if (!e || episode_length < 0) return rr_fail(RR_EINVAL, "rr_env_set_wrappers: bad argument");
+  e->episode_length = episode_length;
+  return RR_OK;
+}
+
+extern "C" int rr_env_set_debug(rr_env *e, float *dbg) {
+  if (!e) return rr_fail(RR_EINVAL, "rr_env_set_debug: null env");
+  e->d_dbg = dbg;
+  return RR_OK;
+}
+extern "C" int rr_env_set_profile(rr_env *e, long long *prof) {
+  if (!e) return rr_fail(RR_EINVAL, "rr_env_set_profile: null env");
+  e->d_prof = prof;
+  return RR_OK;
+}
+
+static int rr_fill_args(rr_env *e, const rr_buffers *b, const float *action, int nsub, int mode, RRStepArgs &a) {
+  if (!e || !b) return rr_fail(RR_EINVAL, "null env / buffers");
+  if (!b->qpos || !b->qvel || !b->qacc_warmstart || (e->model->dev.na > 0 && !b->act))
+    return rr_fail(RR_EINVAL, "rr_buffers: qpos, qvel, act and qacc_warmstart are required");
+  const bool needs_task = b->obs || b->reward || b->metrics;
+  if (needs_task && !e->task.track_pos) return rr_fail(RR_EINVAL, "rr_env_set_task must be called before obs / reward are requested");
+  if (needs_task && !b->cur_frame) return rr_fail(RR_EINVAL, "rr_buffers.cur_frame is required with obs / reward");
+  std::memset(&a, 0, sizeof(a));
+  a.B = e->B; a.nsub = nsub; a.mode = mode; a.action = action;
+  a.qpos = b->qpos; a.qvel = b->qvel; a.act = b->act; a.warm = b->qacc_warmstart; a.time = b->time;
+  a.cur_frame = b->cur_frame;
+  a.in_qpos = b->in_qpos ? b->in_qpos : b->qpos; a.in_qvel = b->in_qvel ? b->in_qvel : b->qvel;
+  a.in_act = b->in_act ? b->in_act : b->act; a.in_warm = b->in_qacc_warmstart ? b->in_qacc_warmstart : b->qacc_warmstart;
+  a.in_time = b->in_time ? b->in_time : b->time; a.in_cur_frame = b->in_cur_frame ? b->in_cur_frame : b->cur_frame;
+  a.in_done = b->in_done ? b->in_done : b->done; a.in_steps = b->in_steps ? b->in_steps : b->steps;
+  a.task = e->task;
+  a.obs = b->obs; a.reward = b->reward; a.done = b->done; a.metrics = b->metrics;
+  a.wrap = e->episode_length > 0;
+  a.episode_length = e->episode_length;
+  if (a.wrap) {
+    if (!b->done || !b->steps || !b->truncation) return rr_fail(RR_EINVAL, "wrappers need done, steps and truncation buffers");
+    if (mode == RR_MODE_STEP && (!b->first_qpos || !b->first_qvel || !b->first_qacc_warmstart ||
+                                 (e->model->dev.na > 0 && !b->first_act) || (b->obs && !b->first_obs)))
+      return rr_fail(RR_EINVAL, "wrappers need the first_* buffers");
+  }
+  a.steps = b->steps; a.truncation = b->truncation;
+  a.first_qpos = b->first_qpos; a.first_qvel = b->first_qvel; a.first_act = b->first_act;
+  a.first_warm = b->first_qacc_warmstart; a.first_time = b->first_time; a.first_obs = b->first_obs;
+  a.xpos = b->xpos; a.xquat = b->xquat; a.subtree_com = b->subtree_com; a.qfrc_actuator = b->qfrc_actuator;
+  a.cinert = b->cinert; a.cvel = b->cvel; a.contact_dist = b->contact_dist; a.qacc = b->qacc; a.niter = b->solver_niter;
+  a.dbg.buf = e->d_dbg;
+  a.dbg.stride = rr_debug_stride_of(e->model->dev);
+  a.prof = e->d_prof;
+  return RR_OK;
+}
+
+extern "C" int rr_env_init(rr_env *e, const rr_buffers *b, void *stream) {
+  RRStepArgs a;
+  int rc = rr_fill_args(e, b, nullptr, 0, RR_MODE_INIT, a);
+  if (rc) return rc;
+  if (rrb_set_device(e->device) || rrb_launch_step(e->model->dev, a, stream)) return rr_fail(RR_ECUDA, rrb_error());
+  g_rr_launches++;
+  return RR_OK;
+}
+
+extern "C" int rr_env_step(rr_env *e, const rr_buffers *b, const float *action, int32_t n_frames, void *stream) {
+  if (n_frames < 1) return rr_fail(RR_EINVAL, "rr_env_step: n_frames must be >= 1");
+  if (!action) return rr_fail(RR_EINVAL, "rr_env_step: null action");
+  RRStepArgs a;
+  int rc = rr_fill_args(e, b, action, n_frames, RR_MODE_STEP, a);
+  if (rc) return rc;
+  if (rrb_set_device(e->device) || rrb_launch_step(e->model->dev, a, stream)) return rr_fail(RR_ECUDA, rrb_error());
+  g_rr_launches++;
+  return RR_OK;
+}
+
+extern "C" int rr_env_step_host(rr_env *e, const rr_buffers *b, const float *action_host, int32_t n_frames, float *obs_host,
+                                float *reward_host, float *done_host, void *stream) {
+  if (!e || !b || !action_host) return rr_fail(RR_EINVAL, "rr_env_step_host: null argument");
+  const RRModelDev &d = e->model->dev;
+  if (rrb_set_device(e->device) || rrb_h2d(e->d_action_stage, action_host, (size_t)e->B * d.nu * sizeof(float), stream))
+    return rr_fail(RR_ECUDA, rrb_error());
+  int rc = rr_env_step(e, b, e->d_action_stage, n_frames, stream);
+  if (rc) return rc;
+  if (obs_host && b->obs && rrb_d2h(obs_host, b->obs, (size_t)e->B * e->model->host.obs_dim * sizeof(float), stream))
+    return rr_fail(RR_ECUDA, rrb_error());
+  if (reward_host && b->reward && rrb_d2h(reward_host, b->reward, (size_t)e->B * sizeof(float), stream))
+    return rr_fail(RR_ECUDA, rrb_error());
+  if (done_host && b->done && rrb_d2h(done_host, b->done, (size_t)e->B * sizeof(float), stream))
+    return rr_fail(RR_ECUDA, rrb_error());
+  if (rrb_sync(stream)) return rr_fail(RR_ECUDA, rrb_error());
+  return RR_OK;
+}
+
+extern "C" int rr_gae(const float *rewards, const float *values, const float *bootstrap_value, const float *termination,
+                      const float *truncation, int32_t T, int32_t B, float discount, float lambda_, float *vs,
+                      float *advantages, void *stream) {
+  if (!rewards || !values || !bootstrap_value || !termination || !truncation || !vs || !advantages || T < 1 || B < 1)
+    return rr_fail(RR_EINVAL, "rr_gae: bad argument");
+  if (rrb_launch_gae(rewards, values, bootstrap_value, termination, truncation, T, B, discount, lambda_, vs, advantages, stream))
+    return rr_fail(RR_ECUDA, rrb_error());
+  g_rr_launches++;
+  return RR_OK;
+}

@@ -1,0 +1,111 @@
+/* rr_device.h -- device-side model tables, shared-memory layout and kernel argument blocks.
+ *
+ * The flat-model blob (include/rr_model_fields.h, produced by brax_rodent_run_b200/mjcf.py) is re-tabulated
+ * by rr_model_build.h into the fp32 / int32 SoA tables below, specialised for what the step kernel needs:
+ * tree levels for the forward scans, the tree-sparse mass-matrix layout (row i = ancestors of dof i in
+ * ascending order, diagonal last), per-pair collision constants with the plane pose folded in, and the
+ * per-contact Jacobian chain offsets.  It replaces the device pytree that the reference gets from
+ * brax.io.mjcf.load_model / mjx.put_model (Rodent_Env_Brax.py:51).
+ */
+#ifndef RR_DEVICE_H_
+#define RR_DEVICE_H_
+
+#include <stdint.h>
+
+/* integer tables: name, expression for the element count (informative) */
+#define RR_DEV_INT_TABLES(X)                                                                              \
+  X(body_parentid) X(body_rootslot) X(body_jntadr) X(body_jntnum) X(level_adr) X(level_body)              \
+  X(jnt_type) X(jnt_qposadr) X(jnt_dofadr) X(jnt_bodyid)                                                  \
+  X(dof_bodyid) X(dof_depth) X(dof_ndesc) X(dof_rowadr) X(M_rowid) X(M_colind)                            \
+  X(act_dofadr) X(act_qposadr) X(act_dyntype) X(act_gaintype) X(act_biastype) X(act_ctrllimited)          \
+  X(act_forcelimited) X(act_actadr)                                                                       \
+  X(pair_fn) X(pair_body) X(pair_conadr) X(pair_lastdof) X(con_pair) X(con_Jadr)                          \
+  X(limit_qposadr) X(limit_dofadr)
+
+#define RR_DEV_FLOAT_TABLES(X)                                                                            \
+  X(body_pos) X(body_quat) X(body_ipos) X(body_iquat) X(body_inertia) X(body_mass)                        \
+  X(jnt_pos) X(jnt_axis) X(jnt_stiffness) X(qpos0) X(qpos_spring)                                         \
+  X(dof_armature) X(dof_damping)                                                                          \
+  X(act_gear) X(act_dynprm) X(act_gainprm) X(act_biasprm) X(act_ctrlrange) X(act_forcerange)              \
+  X(pair_gpos) X(pair_gquat) X(pair_size) X(pair_plane_n) X(pair_plane_p) X(pair_mu) X(pair_solref)       \
+  X(pair_solimp) X(pair_margin) X(pair_invweight)                                                         \
+  X(limit_range) X(limit_margin) X(limit_solref) X(limit_solimp) X(limit_invweight)
+
+/* per-environment shared-memory layout (offsets in floats from the warp's base) */
+struct RRSmem {
+  int qpos, qvel, act, ctrl, actdot;      /* state */
+  int xpos, xquat;                        /* body frames (nbody x 3 / 4) */
+  int com;                                /* nroot x 3 subtree COM of each kinematic tree */
+  int cinert, cdof, cvel;                 /* nbody x 10, nv x 6, nbody x 6 */
+  int M, LD, Dinv;                        /* tree-sparse mass matrix, its LDL' factor, 1/D */
+  int vbuf;                               /* nv staging buffer for mat-vec inputs */
+  int qfrc_act;                           /* nv qfrc_actuator (observation term) */
+  int tmp;                                /* phase-local scratch (see sizes below) */
+  /* aliases inside tmp: */
+  int crb, fcrb;                          /* mass-matrix phase: nbody x 10, nv x 6 */
+  int cacc, cfrc;                         /* rne phase: nbody x 6 each */
+  int con_dist, con_pos, con_frame;       /* constraint phase: ncon, 3 ncon, 9 ncon */
+  int con_J;                              /* 3 x chain per contact, static offsets con_Jadr */
+  int row_D, row_aref, row_Jaref, row_jv; /* nefc each (compact active rows) */
+  int row_id;                             /* nefc ints: limit l -> l ; contact c, k -> nlimit + 4 c + k */
+  int cact;                               /* ncon ints: compact list of active contacts */
+  int total;                              /* floats per environment */
+};
+
+struct RRModelDev {
+  int nq, nv, nu, na, nbody, njnt, ngeom, nM, npair, ncon, nlimit, nefc, nlevel, nroot, nJ;
+  int solver, iterations, ls_iterations;
+  float timestep, gravity[3], tolerance, ls_tolerance, impratio, meaninertia;
+  RRSmem sm;
+#define RR__X(n) const int32_t *n;
+  RR_DEV_INT_TABLES(RR__X)
+#undef RR__X
+#define RR__X(n) const float *n;
+  RR_DEV_FLOAT_TABLES(RR__X)
+#undef RR__X
+};
+
+/* run-task parameters (Rodent_Env_Brax.py:21-35,62-69) */
+struct RRTask {
+  const float *track_pos; /* [track_len, 3] device */
+  int track_len;
+  float ctrl_cost_weight, healthy_reward, healthy_z_lo, healthy_z_hi;
+  int terminate_when_unhealthy;
+};
+
+enum { RR_MODE_STEP = 0, RR_MODE_INIT = 1 };
+
+/* debug dump record layout (floats, per environment): see rr_debug_field() */
+struct RRDebug {
+  float *buf;  /* [B, stride] or null */
+  int stride;
+};
+
+struct RRStepArgs {
+  int B, nsub, mode;
+  const float *action; /* [B, nu] raw policy action; null => zeros */
+  float *qpos, *qvel, *act, *warm, *time; /* in/out state, env-major rows */
+  int *cur_frame;                         /* [B] */
+  const float *in_qpos, *in_qvel, *in_act, *in_warm, *in_time, *in_done, *in_steps; /* null => in place */
+  const int *in_cur_frame;
+  RRTask task;
+  float *obs; /* [B, obs_dim] */
+  float *reward, *done, *metrics; /* [B], [B], [B,3] (pos_reward, reward_quadctrl, reward_alive) */
+  /* fused Brax training wrappers (EpisodeWrapper + AutoResetWrapper); wrap = 0 disables */
+  int wrap, episode_length;
+  float *steps, *truncation; /* [B] */
+  const float *first_qpos, *first_qvel, *first_act, *first_warm, *first_time, *first_obs;
+  /* optional extra outputs of the last forward pass (null = skip) */
+  float *xpos, *xquat, *subtree_com, *qfrc_actuator, *cinert, *cvel, *contact_dist, *qacc;
+  int *niter; /* [B] solver iterations executed in the last substep */
+  RRDebug dbg;
+  long long *prof; /* [B, RR_NPROF] clock64 deltas or null */
+};
+
+enum {
+  RR_PROF_LOAD = 0, RR_PROF_FK, RR_PROF_COM, RR_PROF_CRB, RR_PROF_QM, RR_PROF_FACTOR, RR_PROF_VEL, RR_PROF_RNE,
+  RR_PROF_SMOOTH, RR_PROF_COLLIDE, RR_PROF_CONSTRAINT, RR_PROF_SOLVE_INIT, RR_PROF_SOLVE_LS, RR_PROF_SOLVE_UPD,
+  RR_PROF_EULER, RR_PROF_EPILOGUE, RR_NPROF
+};
+
+#endif /* RR_DEVICE_H_ */

@@ -1,0 +1,303 @@
+/* rr_model_build.h -- host side: flat-model blob -> step-kernel tables (pure C++, no CUDA calls).
+ *
+ * Input is the (dir, idata, fdata) blob described in include/rr_model_fields.h; output is one int32 and one
+ * fp32 buffer holding every table of RRModelDev plus the per-environment shared-memory layout.
+ * The uploader (rr_api.cu) copies the two buffers to the device and fixes the pointers up.
+ */
+#ifndef RR_MODEL_BUILD_H_
+#define RR_MODEL_BUILD_H_
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/rr_model_fields.h"
+#include "rr_device.h"
+
+struct RRHostModel {
+  RRModelDev dev;  /* scalars + layout valid; pointers set by rr_host_model_bind() */
+  std::vector<int32_t> ibuf;
+  std::vector<float> fbuf;
+  /* offsets (in elements) of each table, in X-macro order */
+  std::vector<int> ioff, foff, icount, fcount;
+  int obs_dim;
+};
+
+namespace rr_detail {
+
+struct Blob {
+  const int32_t *dir, *idata;
+  const double *fdata;
+  const int32_t *I(int f) const { return idata + dir[2 * f]; }
+  const double *F(int f) const { return fdata + dir[2 * f]; }
+  int n(int f) const { return dir[2 * f + 1]; }
+};
+
+inline void quat_mul(double *r, const double *a, const double *b) {
+  double w = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
+  double x = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
+  double y = a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1];
+  double z = a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0];
+  r[0] = w; r[1] = x; r[2] = y; r[3] = z;
+}
+inline void quat_rot(double *r, const double *v, const double *q) {
+  double w = q[0], x = q[1], y = q[2], z = q[3];
+  double m[9] = {w * w + x * x - y * y - z * z, 2 * (x * y - w * z), 2 * (x * z + w * y),
+                 2 * (x * y + w * z), w * w - x * x + y * y - z * z, 2 * (y * z - w * x),
+                 2 * (x * z - w * y), 2 * (y * z + w * x), w * w - x * x - y * y + z * z};
+  double a = m[0] * v[0] + m[1] * v[1] + m[2] * v[2];
+  double b = m[3] * v[0] + m[4] * v[1] + m[5] * v[2];
+  double c = m[6] * v[0] + m[7] * v[1] + m[8] * v[2];
+  r[0] = a; r[1] = b; r[2] = c;
+}
+
+}  // namespace rr_detail
+
+#define RR_FID(n) RR_FIELD_##n
+
+/* Build the tables.  Throws std::runtime_error("NotImplemented: ...") for model features outside the
+ * supported subset (mirrors the NotImplementedError that brax.io.mjcf.load_model raises). */
+inline void rr_host_model_build(RRHostModel &hm, const int32_t *dir, const int32_t *idata, int ni, const double *fdata,
+                                int nf) {
+  using namespace rr_detail;
+  (void)ni; (void)nf;
+  Blob B{dir, idata, fdata};
+  RRModelDev &d = hm.dev;
+  std::memset(&d, 0, sizeof(d));
+  const int32_t *oi = B.I(RR_FID(opt_i));
+  const double *of = B.F(RR_FID(opt_f));
+  d.nq = oi[RR_OI_NQ]; d.nv = oi[RR_OI_NV]; d.nu = oi[RR_OI_NU]; d.na = oi[RR_OI_NA]; d.nbody = oi[RR_OI_NBODY];
+  d.njnt = oi[RR_OI_NJNT]; d.ngeom = oi[RR_OI_NGEOM]; d.nM = oi[RR_OI_NM]; d.npair = oi[RR_OI_NPAIR];
+  d.ncon = oi[RR_OI_NCON]; d.nlimit = oi[RR_OI_NLIMIT]; d.nefc = oi[RR_OI_NEFC];
+  d.solver = oi[RR_OI_SOLVER]; d.iterations = oi[RR_OI_ITERATIONS]; d.ls_iterations = oi[RR_OI_LS_ITERATIONS];
+  d.timestep = (float)of[RR_OF_TIMESTEP];
+  d.gravity[0] = (float)of[RR_OF_GRAVITY_X]; d.gravity[1] = (float)of[RR_OF_GRAVITY_Y]; d.gravity[2] = (float)of[RR_OF_GRAVITY_Z];
+  d.tolerance = (float)of[RR_OF_TOLERANCE]; d.ls_tolerance = (float)of[RR_OF_LS_TOLERANCE];
+  d.impratio = (float)of[RR_OF_IMPRATIO]; d.meaninertia = (float)of[RR_OF_MEANINERTIA];
+  const int nq = d.nq, nv = d.nv, nu = d.nu, nb = d.nbody, nj = d.njnt, nM = d.nM, np = d.npair, nc = d.ncon, nl = d.nlimit;
+  if (nv > 160) throw std::runtime_error("NotImplemented: nv > 160");
+  if (d.na != nu && d.na != 0) {
+    /* mixed stateful / stateless actuators are fine; nothing to check */
+  }
+
+  std::vector<std::vector<int32_t>> IT;
+  std::vector<std::vector<float>> FT;
+#define RR__X(n) std::vector<int32_t> t_##n;
+  RR_DEV_INT_TABLES(RR__X)
+#undef RR__X
+#define RR__X(n) std::vector<float> t_##n;
+  RR_DEV_FLOAT_TABLES(RR__X)
+#undef RR__X
+
+  auto cpI = [&](std::vector<int32_t> &dst, int f) { dst.assign(B.I(f), B.I(f) + B.n(f)); };
+  auto cpF = [&](std::vector<float> &dst, int f) {
+    dst.resize(B.n(f));
+    for (int i = 0; i < B.n(f); i++) dst[i] = (float)B.F(f)[i];
+  };
+
+  /* ---- bodies ---- */
+  cpI(t_body_parentid, RR_FID(body_parentid));
+  cpI(t_body_jntadr, RR_FID(body_jntadr));
+  cpI(t_body_jntnum, RR_FID(body_jntnum));
+  cpF(t_body_pos, RR_FID(body_pos)); cpF(t_body_quat, RR_FID(body_quat)); cpF(t_body_ipos, RR_FID(body_ipos));
+  cpF(t_body_iquat, RR_FID(body_iquat)); cpF(t_body_inertia, RR_FID(body_inertia)); cpF(t_body_mass, RR_FID(body_mass));
+  const int32_t *rootid = B.I(RR_FID(body_rootid)), *parent = B.I(RR_FID(body_parentid)), *lastdof = B.I(RR_FID(body_lastdof));
+  /* kinematic-tree roots (world excluded): slot index per body; world gets slot 0 (its cinert is zero anyway) */
+  std::vector<int> roots;
+  t_body_rootslot.assign(nb, 0);
+  for (int b = 1; b < nb; b++) {
+    int r = rootid[b];
+    auto it = std::find(roots.begin(), roots.end(), r);
+    if (it == roots.end()) { roots.push_back(r); it = roots.end() - 1; }
+    t_body_rootslot[b] = (int)(it - roots.begin());
+  }
+  d.nroot = std::max<int>(1, (int)roots.size());
+  /* tree levels (level 0 = world) */
+  std::vector<int> depth(nb, 0);
+  int maxd = 0;
+  for (int b = 1; b < nb; b++) { depth[b] = depth[parent[b]] + 1; maxd = std::max(maxd, depth[b]); }
+  d.nlevel = maxd + 1;
+  t_level_adr.assign(d.nlevel + 1, 0);
+  for (int lev = 1; lev <= maxd; lev++) {
+    t_level_adr[lev] = (int)t_level_body.size();
+    for (int b = 1; b < nb; b++) if (depth[b] == lev) t_level_body.push_back(b);
+  }
+  t_level_adr[0] = 0;
+  t_level_adr[d.nlevel] = (int)t_level_body.size();
+  if (t_level_body.empty()) t_level_body.push_back(0);
+
+  /* ---- joints ---- */
+  cpI(t_jnt_type, RR_FID(jnt_type)); cpI(t_jnt_qposadr, RR_FID(jnt_qposadr)); cpI(t_jnt_dofadr, RR_FID(jnt_dofadr));
+  cpI(t_jnt_bodyid, RR_FID(jnt_bodyid));
+  cpF(t_jnt_pos, RR_FID(jnt_pos)); cpF(t_jnt_axis, RR_FID(jnt_axis)); cpF(t_jnt_stiffness, RR_FID(jnt_stiffness));
+  cpF(t_qpos0, RR_FID(qpos0)); cpF(t_qpos_spring, RR_FID(qpos_spring));
+  for (int j = 0; j < nj; j++)
+    if (t_jnt_type[j] != RR_JNT_FREE && t_jnt_type[j] != RR_JNT_HINGE) throw std::runtime_error("NotImplemented: ball/slide joints");
+
+  /* ---- dofs + tree-sparse layout ---- */
+  cpI(t_dof_bodyid, RR_FID(dof_bodyid));
+  cpI(t_dof_rowadr, RR_FID(M_rowadr));
+  cpI(t_M_colind, RR_FID(M_colind));
+  cpF(t_dof_armature, RR_FID(dof_armature)); cpF(t_dof_damping, RR_FID(dof_damping));
+  const int32_t *dofparent = B.I(RR_FID(dof_parentid)), *rownnz = B.I(RR_FID(M_rownnz));
+  t_dof_depth.assign(nv, 0);
+  t_dof_ndesc.assign(nv, 0);
+  for (int i = 0; i < nv; i++) {
+    t_dof_depth[i] = rownnz[i] - 1;
+    for (int k = dofparent[i]; k >= 0; k = dofparent[k]) t_dof_ndesc[k]++;
+  }
+  /* descendants of a dof must be the contiguous range (i, i + ndesc]: DFS numbering */
+  for (int i = 0; i < nv; i++)
+    for (int k = i + 1; k < nv; k++) {
+      bool anc = false;
+      for (int a = dofparent[k]; a >= 0; a = dofparent[a]) if (a == i) anc = true;
+      if (anc != (k <= i + t_dof_ndesc[i])) throw std::runtime_error("internal: dof numbering is not depth-first");
+    }
+  t_M_rowid.assign(nM, 0);
+  for (int i = 0; i < nv; i++)
+    for (int t = 0; t < rownnz[i]; t++) t_M_rowid[t_dof_rowadr[i] + t] = i;
+  if (t_M_rowid.empty()) { t_M_rowid.push_back(0); t_M_colind.push_back(0); }
+
+  /* ---- actuators ---- */
+  const int32_t *ajnt = B.I(RR_FID(actuator_jntid));
+  t_act_dofadr.resize(nu); t_act_qposadr.resize(nu);
+  std::vector<int> used(nv, 0);
+  for (int u = 0; u < nu; u++) {
+    t_act_dofadr[u] = t_jnt_dofadr[ajnt[u]];
+    t_act_qposadr[u] = t_jnt_qposadr[ajnt[u]];
+    if (used[t_act_dofadr[u]]++) throw std::runtime_error("NotImplemented: two actuators on one joint");
+  }
+  cpI(t_act_dyntype, RR_FID(actuator_dyntype)); cpI(t_act_gaintype, RR_FID(actuator_gaintype));
+  cpI(t_act_biastype, RR_FID(actuator_biastype)); cpI(t_act_ctrllimited, RR_FID(actuator_ctrllimited));
+  cpI(t_act_forcelimited, RR_FID(actuator_forcelimited)); cpI(t_act_actadr, RR_FID(actuator_actadr));
+  cpF(t_act_gear, RR_FID(actuator_gear)); cpF(t_act_dynprm, RR_FID(actuator_dynprm));
+  cpF(t_act_gainprm, RR_FID(actuator_gainprm)); cpF(t_act_biasprm, RR_FID(actuator_biasprm));
+  cpF(t_act_ctrlrange, RR_FID(actuator_ctrlrange)); cpF(t_act_forcerange, RR_FID(actuator_forcerange));
+
+  /* ---- collision pairs: plane (on a static body) vs sphere / capsule / ellipsoid ---- */
+  const int32_t *g1 = B.I(RR_FID(pair_geom1)), *g2 = B.I(RR_FID(pair_geom2)), *gbody = B.I(RR_FID(geom_bodyid));
+  const double *gpos = B.F(RR_FID(geom_pos)), *gquat = B.F(RR_FID(geom_quat)), *gsize = B.F(RR_FID(geom_size));
+  const double *bpos = B.F(RR_FID(body_pos)), *bquat = B.F(RR_FID(body_quat)), *binvw = B.F(RR_FID(body_invweight0));
+  cpI(t_pair_fn, RR_FID(pair_fn)); cpI(t_pair_conadr, RR_FID(pair_conadr));
+  cpF(t_pair_mu, RR_FID(pair_friction)); cpF(t_pair_solref, RR_FID(pair_solref)); cpF(t_pair_solimp, RR_FID(pair_solimp));
+  cpF(t_pair_margin, RR_FID(pair_includemargin));
+  t_pair_body.resize(np); t_pair_lastdof.resize(np); t_pair_gpos.resize(3 * np); t_pair_gquat.resize(4 * np);
+  t_pair_size.resize(3 * np); t_pair_plane_n.resize(3 * np); t_pair_plane_p.resize(3 * np); t_pair_invweight.resize(np);
+  t_con_pair.assign(std::max(nc, 1), 0); t_con_Jadr.assign(std::max(nc, 1), 0);
+  int nJ = 0;
+  for (int p = 0; p < np; p++) {
+    int bp = gbody[g1[p]], b2 = gbody[g2[p]];
+    if (lastdof[bp] >= 0) throw std::runtime_error("NotImplemented: collision plane on a moving body");
+    if (lastdof[b2] < 0) throw std::runtime_error("NotImplemented: collision geom on a static body");
+    /* world pose of the static plane: compose up the (static) body chain */
+    double pq[4] = {1, 0, 0, 0}, pp[3] = {0, 0, 0};
+    std::vector<int> chain;
+    for (int b = bp; b > 0; b = parent[b]) chain.push_back(b);
+    for (int k = (int)chain.size() - 1; k >= 0; k--) {
+      int b = chain[k];
+      double r[3], q[4];
+      quat_rot(r, bpos + 3 * b, pq);
+      for (int c = 0; c < 3; c++) pp[c] += r[c];
+      quat_mul(q, pq, bquat + 4 * b);
+      std::memcpy(pq, q, sizeof(q));
+    }
+    double r[3], q[4], z[3] = {0, 0, 1}, n[3];
+    quat_rot(r, gpos + 3 * g1[p], pq);
+    quat_mul(q, pq, gquat + 4 * g1[p]);
+    quat_rot(n, z, q);
+    for (int c = 0; c < 3; c++) {
+      t_pair_plane_p[3 * p + c] = (float)(pp[c] + r[c]);
+      t_pair_plane_n[3 * p + c] = (float)n[c];
+      t_pair_gpos[3 * p + c] = (float)gpos[3 * g2[p] + c];
+      t_pair_size[3 * p + c] = (float)gsize[3 * g2[p] + c];
+    }
+    for (int c = 0; c < 4; c++) t_pair_gquat[4 * p + c] = (float)gquat[4 * g2[p] + c];
+    t_pair_body[p] = b2;
+    t_pair_lastdof[p] = lastdof[b2];
+    t_pair_invweight[p] = (float)(binvw[2 * bp] + binvw[2 * b2]);
+    int cend = (p + 1 < np) ? t_pair_conadr[p + 1] : nc;
+    for (int c = t_pair_conadr[p]; c < cend; c++) {
+      t_con_pair[c] = p;
+      t_con_Jadr[c] = nJ;
+      nJ += 3 * (t_dof_depth[lastdof[b2]] + 1);
+    }
+  }
+  d.nJ = nJ;
+
+  /* ---- joint limits ---- */
+  const int32_t *ljnt = B.I(RR_FID(limit_jntid));
+  const double *jrange = B.F(RR_FID(jnt_range)), *jmargin = B.F(RR_FID(jnt_margin)), *jsolref = B.F(RR_FID(jnt_solref)),
+               *jsolimp = B.F(RR_FID(jnt_solimp)), *dinvw = B.F(RR_FID(dof_invweight0));
+  t_limit_qposadr.resize(nl); t_limit_dofadr.resize(nl); t_limit_range.resize(2 * nl); t_limit_margin.resize(nl);
+  t_limit_solref.resize(2 * nl); t_limit_solimp.resize(5 * nl); t_limit_invweight.resize(nl);
+  for (int l = 0; l < nl; l++) {
+    int j = ljnt[l];
+    t_limit_qposadr[l] = t_jnt_qposadr[j];
+    t_limit_dofadr[l] = t_jnt_dofadr[j];
+    t_limit_range[2 * l] = (float)jrange[2 * j]; t_limit_range[2 * l + 1] = (float)jrange[2 * j + 1];
+    t_limit_margin[l] = (float)jmargin[j];
+    for (int k = 0; k < 2; k++) t_limit_solref[2 * l + k] = (float)jsolref[2 * j + k];
+    for (int k = 0; k < 5; k++) t_limit_solimp[5 * l + k] = (float)jsolimp[5 * j + k];
+    t_limit_invweight[l] = (float)dinvw[t_jnt_dofadr[j]];
+  }
+
+  /* ---- pack ---- */
+  hm.ibuf.clear(); hm.fbuf.clear(); hm.ioff.clear(); hm.foff.clear(); hm.icount.clear(); hm.fcount.clear();
+  auto padI = [&]() { while (hm.ibuf.size() % 4) hm.ibuf.push_back(0); };
+  auto padF = [&]() { while (hm.fbuf.size() % 4) hm.fbuf.push_back(0.f); };
+#define RR__X(n)                                                   \
+  hm.ioff.push_back((int)hm.ibuf.size());                          \
+  hm.icount.push_back((int)t_##n.size());                          \
+  hm.ibuf.insert(hm.ibuf.end(), t_##n.begin(), t_##n.end());       \
+  padI();
+  RR_DEV_INT_TABLES(RR__X)
+#undef RR__X
+#define RR__X(n)                                                   \
+  hm.foff.push_back((int)hm.fbuf.size());                          \
+  hm.fcount.push_back((int)t_##n.size());                          \
+  hm.fbuf.insert(hm.fbuf.end(), t_##n.begin(), t_##n.end());       \
+  padF();
+  RR_DEV_FLOAT_TABLES(RR__X)
+#undef RR__X
+  if (hm.ibuf.empty()) hm.ibuf.push_back(0);
+  if (hm.fbuf.empty()) hm.fbuf.push_back(0.f);
+
+  /* ---- shared-memory layout ---- */
+  RRSmem &s = d.sm;
+  int o = 0;
+  auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };
+  s.qpos = take(nq); s.qvel = take(nv); s.act = take(d.na); s.ctrl = take(nu); s.actdot = take(d.na);
+  s.xpos = take(3 * nb); s.xquat = take(4 * nb); s.com = take(3 * d.nroot);
+  s.cinert = take(10 * nb); s.cdof = take(6 * nv); s.cvel = take(6 * nb);
+  s.M = take(nM); s.LD = take(nM); s.Dinv = take(nv); s.vbuf = take(nv); s.qfrc_act = take(nv);
+  s.tmp = o;
+  int t0 = o, tmax = o;
+  /* mass-matrix phase */
+  o = t0; s.crb = take(10 * nb); s.fcrb = take(6 * nv); tmax = std::max(tmax, o);
+  /* rne phase */
+  o = t0; s.cacc = take(6 * nb); s.cfrc = take(6 * nb); tmax = std::max(tmax, o);
+  /* constraint + solver phase */
+  o = t0; s.con_dist = take(nc); s.con_pos = take(3 * nc); s.con_frame = take(9 * nc); s.con_J = take(nJ);
+  s.row_D = take(d.nefc); s.row_aref = take(d.nefc); s.row_Jaref = take(d.nefc); s.row_jv = take(d.nefc);
+  s.row_id = take(d.nefc); s.cact = take(nc); tmax = std::max(tmax, o);
+  s.total = tmax;
+
+  hm.obs_dim = nq + nv + 10 * (nb - 1) + 6 * (nb - 1) + nv + 3; /* Rodent_Env_Brax.py:149-158 */
+}
+
+/* Point the table pointers of `dev` at copies of ibuf / fbuf living at ibase / fbase. */
+inline void rr_host_model_bind(const RRHostModel &hm, RRModelDev &dev, const int32_t *ibase, const float *fbase) {
+  int k = 0;
+#define RR__X(n) dev.n = ibase + hm.ioff[k++];
+  RR_DEV_INT_TABLES(RR__X)
+#undef RR__X
+  k = 0;
+#define RR__X(n) dev.n = fbase + hm.foff[k++];
+  RR_DEV_FLOAT_TABLES(RR__X)
+#undef RR__X
+}
+
+#endif /* RR_MODEL_BUILD_H_ */

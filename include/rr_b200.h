@@ -1,0 +1,124 @@
+/* rr_b200.h -- C ABI of the B200 rodent step library (librr_b200.so).
+ *
+ * This is the drop-in boundary for the reference's data-parallel hot path.  Each entry point names the
+ * reference interface it replaces (file:line in talmolab/Brax-Rodent-Run); the Python class
+ * brax_rodent_run_b200.Rodent binds these with ctypes and mirrors Rodent_Env_Brax.py's surface.
+ * Plain pointers and sizes only; all `float *` / `int32_t *` members of rr_buffers are DEVICE pointers
+ * into caller-owned, env-major (row per environment) arrays; work is enqueued on the caller's CUDA
+ * stream (`stream` is a cudaStream_t passed as void *) and nothing synchronises unless stated.
+ *
+ * Return value: 0 on success, otherwise an RR_E* code; rr_last_error() gives the message.
+ *   RR_EINVAL  -> Python raises ValueError        (bad arguments / bad model blob)
+ *   RR_ENOTIMPL-> Python raises NotImplementedError (model feature outside the supported subset, as
+ *                 brax.io.mjcf.load_model does, Rodent_Env_Brax.py:51)
+ *   RR_ECUDA   -> Python raises RuntimeError
+ */
+#ifndef RR_B200_H_
+#define RR_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { RR_OK = 0, RR_EINVAL = 1, RR_ENOTIMPL = 2, RR_ECUDA = 3 };
+
+typedef struct rr_model rr_model;
+typedef struct rr_env rr_env;
+
+typedef struct rr_dims {
+  int32_t nq, nv, nu, na, nbody, njnt, ngeom, ncon, nlimit, nefc, nM, nroot;
+  int32_t obs_dim;       /* nq + nv + 10 (nbody-1) + 6 (nbody-1) + nv + 3, Rodent_Env_Brax.py:149-158 */
+  int32_t smem_bytes;    /* shared memory per environment (one warp) */
+  int32_t debug_stride;  /* floats per environment of the debug record */
+  float timestep;        /* mj_model.opt.timestep */
+} rr_dims;
+
+/* Caller-owned device arrays, one row per environment.  Null members are skipped where marked optional. */
+typedef struct rr_buffers {
+  /* persistent physics state = the fields of mjx.Data that the next step reads */
+  float *qpos;            /* [B, nq]  */
+  float *qvel;            /* [B, nv]  */
+  float *act;             /* [B, na]  */
+  float *qacc_warmstart;  /* [B, nv]  */
+  float *time;            /* [B] optional */
+  int32_t *cur_frame;     /* [B] state.info["cur_frame"], Rodent_Env_Brax.py:77-79,103-104 */
+  /* Optional separate INPUT arrays (functional style, as the reference's immutable State): when non-null the
+   * step reads the previous state from these and writes the new one to the members above; when null the
+   * members above are updated in place. */
+  const float *in_qpos, *in_qvel, *in_act, *in_qacc_warmstart, *in_time;
+  const int32_t *in_cur_frame;
+  const float *in_done, *in_steps; /* previous done / steps for the fused wrappers */
+  /* step outputs (State fields) */
+  float *obs;             /* [B, obs_dim] optional */
+  float *reward;          /* [B] optional */
+  float *done;            /* [B] optional; required (read as previous done) when wrappers are on */
+  float *metrics;         /* [B, 3] pos_reward, reward_quadctrl, reward_alive; optional */
+  /* brax EpisodeWrapper / AutoResetWrapper state (required when rr_env_set_wrappers(len > 0)) */
+  float *steps;           /* [B] info["steps"] */
+  float *truncation;      /* [B] info["truncation"] */
+  const float *first_qpos, *first_qvel, *first_act, *first_qacc_warmstart, *first_time, *first_obs;
+  /* optional views of the last forward pass (pipeline_state attributes) */
+  float *xpos;            /* [B, nbody, 3] */
+  float *xquat;           /* [B, nbody, 4] */
+  float *subtree_com;     /* [B, nroot, 3] */
+  float *qfrc_actuator;   /* [B, nv] */
+  float *cinert;          /* [B, nbody, 10] */
+  float *cvel;            /* [B, nbody, 6] */
+  float *contact_dist;    /* [B, ncon] */
+  float *qacc;            /* [B, nv] */
+  int32_t *solver_niter;  /* [B] */
+} rr_buffers;
+
+const char *rr_last_error(void);
+
+/* Model: replaces mujoco.MjModel.from_xml_path + brax.io.mjcf.load_model (Rodent_Env_Brax.py:41,51).
+ * Input is the flat-model blob of include/rr_model_fields.h produced by brax_rodent_run_b200.mjcf. */
+int rr_model_create(const int32_t *dir, int32_t ndir, const int32_t *idata, int32_t ni, const double *fdata,
+                    int32_t nf, rr_model **out);
+void rr_model_destroy(rr_model *m);
+/* mj_model.opt.solver / iterations / ls_iterations (Rodent_Env_Brax.py:42-47); solver: 0 = CG */
+int rr_model_set_solver(rr_model *m, int32_t solver, int32_t iterations, int32_t ls_iterations);
+int rr_model_dims(const rr_model *m, rr_dims *out);
+
+/* Environment batch on one GPU: replaces PipelineEnv.__init__ (Rodent_Env_Brax.py:60) + VmapWrapper. */
+int rr_env_create(const rr_model *m, int32_t num_envs, int32_t device, rr_env **out);
+void rr_env_destroy(rr_env *e);
+/* Run-task constants (Rodent_Env_Brax.py:62-69); track_pos is a HOST array [track_len, 3], copied. */
+int rr_env_set_task(rr_env *e, const float *track_pos, int32_t track_len, float ctrl_cost_weight, float healthy_reward,
+                    float healthy_z_lo, float healthy_z_hi, int32_t terminate_when_unhealthy);
+/* brax EpisodeWrapper(episode_length, action_repeat=1) + AutoResetWrapper fused into the step; 0 = off */
+int rr_env_set_wrappers(rr_env *e, int32_t episode_length);
+
+/* pipeline_init + _get_obs of Rodent.reset (Rodent_Env_Brax.py:87-95): mjx.forward at (qpos, qvel) with
+ * act = ctrl = 0 is the caller's job to zero; writes normalised qpos, qacc_warmstart, obs, zero reward/done/metrics. */
+int rr_env_init(rr_env *e, const rr_buffers *b, void *stream);
+/* Rodent.step (Rodent_Env_Brax.py:98-136): n_frames x mjx.step with ctrl = action, reward, done, metrics, obs
+ * (+ the fused wrappers when enabled).  action: DEVICE [B, nu]. */
+int rr_env_step(rr_env *e, const rr_buffers *b, const float *action, int32_t n_frames, void *stream);
+/* Same step through HOST buffers: copies action host->device, runs the step, copies obs / reward / done back and
+ * synchronises the stream.  This is the call the end-to-end benchmark times. */
+int rr_env_step_host(rr_env *e, const rr_buffers *b, const float *action_host, int32_t n_frames, float *obs_host,
+                     float *reward_host, float *done_host, void *stream);
+
+/* ppo.losses.compute_gae (brax, called inside ppo.train from brax_rodent_run_ppo.py:200).  All DEVICE,
+ * time-major: rewards/values/termination/truncation [T, B], bootstrap [B]; outputs vs, advantages [T, B]. */
+int rr_gae(const float *rewards, const float *values, const float *bootstrap_value, const float *termination,
+           const float *truncation, int32_t T, int32_t B, float discount, float lambda_, float *vs, float *advantages,
+           void *stream);
+
+/* Parity-test hooks: per-environment dump of forward-pass intermediates (tests only). */
+int rr_debug_field(const rr_model *m, const char *name, int32_t *offset, int32_t *count);
+int rr_env_set_debug(rr_env *e, float *dbg /* DEVICE [B, debug_stride] or null */);
+/* Per-phase clock64 accumulation (profiling builds of bench.py); prof: DEVICE int64 [B, rr_prof_count()] or null */
+int rr_env_set_profile(rr_env *e, long long *prof);
+int rr_prof_count(void);
+const char *rr_prof_name(int32_t i);
+/* number of kernels launched by this library since load (bench.py's gpu_launches) */
+long long rr_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RR_B200_H_ */

@@ -1,0 +1,157 @@
+/* rr_emu.cpp -- TEST INFRASTRUCTURE ONLY: host build of the step-kernel text with the 32 lanes run as fibers.
+ *
+ * There is no GPU in the development container, so the device code in brax_rodent_run_b200/csrc/rr_kernels.inl
+ * is written against a handful of warp primitives (__shfl_sync, __shfl_xor_sync, __ballot_sync, __syncwarp,
+ * __ldg).  This file supplies those primitives on the host: the 32 lanes of an environment's warp are ucontext
+ * fibers scheduled round-robin, every primitive is a yield point, and exchanged values go through a
+ * double-buffered slot array.  It exports the same C ABI as librr_b200.so (include/rr_b200.h) with "device"
+ * pointers being host pointers, so tests/ can drive the identical host logic + kernel text on the CPU and compare
+ * it with the oracle.  It is NOT a CPU fallback: the product package never loads it (the Python layer refuses
+ * to run without the CUDA library unless a test passes the emulator handle explicitly).
+ */
+#ifndef _GNU_SOURCE
+#define _GNU_SOURCE
+#endif
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <ucontext.h>
+
+#include <vector>
+
+/* ---- warp emulation ---------------------------------------------------------------------------------- */
+namespace emu {
+static const int NL = 32;
+static ucontext_t g_sched, g_fib[NL];
+static int g_lane = 0;
+static bool g_done[NL];
+static int g_par[NL];
+static uint32_t g_slot[2][NL];
+static int g_tag[2][NL];
+static std::vector<char> g_stacks;
+static void (*g_body)(int lane, void *arg);
+static void *g_arg;
+
+static inline void yield() { swapcontext(&g_fib[g_lane], &g_sched); }
+
+static inline uint32_t exchange(uint32_t v, int src, int tag) {
+  int l = g_lane, p = g_par[l];
+  g_slot[p][l] = v;
+  g_tag[p][l] = tag;
+  g_par[l] ^= 1;
+  yield();
+  if (g_tag[p][src & 31] != tag) { fprintf(stderr, "emu: lanes diverged at a warp collective (tag %d vs %d)\n", tag, g_tag[p][src & 31]); abort(); }
+  return g_slot[p][src & 31];
+}
+
+static void trampoline() {
+  int l = g_lane;
+  g_body(l, g_arg);
+  g_done[l] = true;
+  swapcontext(&g_fib[l], &g_sched);
+}
+
+static void run_warp(void (*body)(int, void *), void *arg) {
+  const size_t STK = 512 * 1024;
+  if (g_stacks.size() < STK * NL) g_stacks.resize(STK * NL);
+  g_body = body;
+  g_arg = arg;
+  for (int l = 0; l < NL; l++) {
+    getcontext(&g_fib[l]);
+    g_fib[l].uc_stack.ss_sp = g_stacks.data() + STK * l;
+    g_fib[l].uc_stack.ss_size = STK;
+    g_fib[l].uc_link = &g_sched;
+    makecontext(&g_fib[l], trampoline, 0);
+    g_done[l] = false;
+    g_par[l] = 0;
+  }
+  for (;;) {
+    int alive = 0;
+    for (int l = 0; l < NL; l++) {
+      if (g_done[l]) continue;
+      g_lane = l;
+      swapcontext(&g_sched, &g_fib[l]);
+      alive++;
+    }
+    if (!alive) break;
+  }
+}
+}  // namespace emu
+
+static inline uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+static inline float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+
+static inline float __shfl_sync(unsigned, float v, int src) { return u2f(emu::exchange(f2u(v), src, 1)); }
+static inline int __shfl_sync(unsigned, int v, int src) { return (int)emu::exchange((uint32_t)v, src, 2); }
+static inline float __shfl_xor_sync(unsigned, float v, int mask) { return u2f(emu::exchange(f2u(v), emu::g_lane ^ mask, 3)); }
+static inline unsigned __ballot_sync(unsigned, bool pred) {
+  int l = emu::g_lane, p = emu::g_par[l];
+  emu::g_slot[p][l] = pred ? 1u : 0u;
+  emu::g_tag[p][l] = 4;
+  emu::g_par[l] ^= 1;
+  emu::yield();
+  unsigned r = 0;
+  for (int k = 0; k < 32; k++) {
+    if (emu::g_tag[p][k] != 4) { fprintf(stderr, "emu: lanes diverged at ballot\n"); abort(); }
+    r |= emu::g_slot[p][k] << k;
+  }
+  return r;
+}
+static inline void __syncwarp() { emu::exchange(0, emu::g_lane, 5); }
+static inline int __popc(unsigned x) { return __builtin_popcount(x); }
+
+#define RR_DEV static inline
+#define RR_HOSTDEV static inline
+#define RR_DEV_MEMBER inline
+#define RR_LDG(p) (*(p))
+#define RR_CLOCK() 0LL
+
+#include "../../brax_rodent_run_b200/csrc/rr_kernels.inl"
+
+/* ---- host backend for the shared C-ABI body ------------------------------------------------------------- */
+static const char *rrb_error() { return "emulator backend error"; }
+static int rrb_set_device(int) { return 0; }
+static int rrb_malloc(void **p, size_t bytes) { *p = calloc(bytes ? bytes : 4, 1); return *p ? 0 : 1; }
+static void rrb_free(void *p) { free(p); }
+static int rrb_h2d(void *dst, const void *src, size_t bytes, void *) { memcpy(dst, src, bytes); return 0; }
+static int rrb_d2h(void *dst, const void *src, size_t bytes, void *) { memcpy(dst, src, bytes); return 0; }
+static int rrb_sync(void *) { return 0; }
+
+struct EmuJob { const RRModelDev *m; const RRStepArgs *a; int env; float *sm; };
+template <int NS>
+static void emu_lane(int lane, void *arg) {
+  EmuJob *j = (EmuJob *)arg;
+  rr::env_run<NS>(*j->m, *j->a, j->env, j->sm, lane);
+}
+static int rrb_launch_step(const RRModelDev &m, const RRStepArgs &a, void *) {
+  std::vector<float> sm((size_t)m.sm.total + 16);
+  for (int env = 0; env < a.B; env++) {
+    /* poison shared memory so that reads of unwritten slots show up as NaN */
+    for (auto &x : sm) x = NAN;
+    EmuJob j{&m, &a, env, sm.data()};
+    emu::run_warp(m.nv <= 96 ? emu_lane<3> : emu_lane<5>, &j);
+  }
+  return 0;
+}
+static int rrb_launch_gae(const float *rewards, const float *values, const float *bootstrap, const float *termination,
+                          const float *truncation, int T, int B, float discount, float lambda_, float *vs, float *adv, void *) {
+  for (int b = 0; b < B; b++) {
+    float acc = 0.f, v_next = bootstrap[b], vs_next = bootstrap[b];
+    for (int t = T - 1; t >= 0; t--) {
+      size_t i = (size_t)t * B + b;
+      float mask = 1.f - truncation[i], term = termination[i], v = values[i], r = rewards[i];
+      float delta = (r + discount * (1.f - term) * v_next - v) * mask;
+      acc = delta + discount * (1.f - term) * mask * lambda_ * acc;
+      float vs_t = acc + v;
+      adv[i] = (r + discount * (1.f - term) * vs_next - v) * mask;
+      vs[i] = vs_t;
+      v_next = v;
+      vs_next = vs_t;
+    }
+  }
+  return 0;
+}
+
+#include "../../brax_rodent_run_b200/csrc/rr_api_impl.inl"

@@ -1,0 +1,80 @@
+"""mjx.forward parity: every intermediate of the CUDA path (through the C ABI's debug record) against the CPU
+oracle on the same seeded inputs.  `emu` runs the same kernel text on the host (no GPU needed); `cuda` is the
+product library on a B200.  Tolerances are relative to the largest magnitude of the reference array (fp32 path
+vs fp64 oracle): 2e-5 for quantities before the solver, 1e-4 for solver outputs (north_star bound)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import backend_params, load_asset, synthetic_track
+
+PRE_SOLVER = ("xpos", "xquat", "cinert", "cdof", "cvel", "qfrc_bias", "qfrc_passive", "qfrc_actuator", "qfrc_smooth",
+              "qacc_smooth", "contact_dist", "contact_pos", "contact_frame", "efc_J", "efc_aref")
+POST_SOLVER = ("efc_force", "qacc", "qfrc_constraint")
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64).ravel(), np.asarray(b, np.float64).ravel()
+    return np.abs(a - b).max() / (np.abs(b).max() + 1e-30)
+
+
+def make_inputs(m, B, seed):
+    rng = np.random.default_rng(seed)
+    qpos = np.tile(m.qpos0, (B, 1)) + rng.uniform(-.05, .05, (B, m.nq))
+    qpos[:, 2] = rng.uniform(0.0, 0.08, B)                 # from deep penetration to airborne
+    qpos[:, 3:7] += rng.uniform(-.3, .3, (B, 4))           # un-normalised root quaternion (written back normalised)
+    lim = rng.integers(7, m.nq, (B, 6))
+    for e in range(B):
+        qpos[e, lim[e]] += rng.choice([-1.5, 1.5], 6)      # push some hinges through their limits
+    qvel = rng.uniform(-1, 1, (B, m.nv))
+    return qpos, qvel
+
+
+@pytest.mark.parametrize("backend", backend_params())
+@pytest.mark.parametrize("model_name,iters", [("rodent_0", 4), ("rodent_0", 8), ("rodent_new", 6), ("rodent_pair", 4)])
+def test_forward_intermediates(backend, model_name, iters, make_env, oracle_mod):
+    from brax_rodent_run_b200 import model_blob
+    m = load_asset(model_name)
+    B = 3 if backend == "emu" else 16
+    env = make_env(backend, synthetic_track(), num_envs=B, model=m, iterations=iters, ls_iterations=iters)
+    qpos, qvel = make_inputs(m, B, seed=iters)
+    out = env.debug_forward(torch.tensor(qpos), torch.tensor(qvel))
+    out = {k: v.cpu().numpy() for k, v in out.items()}
+    blob = model_blob.pack(m)
+    for e in range(min(B, 4)):
+        o = oracle_mod.Oracle(blob, "f64")
+        o.set_options(0, iters, iters)
+        o.init(qpos[e], qvel[e])
+        # root quaternion is written back normalised (SURVEY section 4 KAT v)
+        assert abs(np.linalg.norm(out["qpos"][e, 3:7]) - 1) < 1e-6
+        assert rel(out["qpos"][e], o.get("qpos")) < 1e-6
+        for k in PRE_SOLVER:
+            assert rel(out[k][e], o.get(k)) < 2e-5, (k, e, rel(out[k][e], o.get(k)))
+        # tree-sparse qM against the oracle's dense one
+        M = o.get("qM").reshape(m.nv, m.nv)
+        dense = np.array([M[i, m.M_colind[m.M_rowadr[i] + t]] for i in range(m.nv) for t in range(m.M_rownnz[i])])
+        assert rel(out["qM_sparse"][e], dense) < 1e-5
+        # efc_D: inactive rows are 1/mjMINVAL in both
+        assert rel(np.log(out["efc_D"][e]), np.log(o.get("efc_D"))) < 1e-5
+        # active sets must match exactly (contacts: dist < 0; rows: J != 0)
+        act_k = np.abs(out["efc_J"][e].reshape(m.nefc, m.nv)).sum(1) > 0
+        act_o = np.abs(o.get("efc_J").reshape(m.nefc, m.nv)).sum(1) > 0
+        assert (act_k == act_o).all()
+        # the CG exit test (improvement / gradient < tolerance) is rounding-sensitive: fp32 may run one more or one
+        # fewer iteration than the fp64 oracle; the result must agree regardless
+        assert abs(int(out["scalars"][e, 0]) - int(o.scalar("solver_niter"))) <= 1
+        for k in POST_SOLVER:
+            assert rel(out[k][e], o.get(k)) < 1e-4, (k, e, rel(out[k][e], o.get(k)))
+        assert rel(out["qacc_warmstart"][e], o.get("qacc_warmstart")) < 1e-4
+
+
+@pytest.mark.parametrize("backend", backend_params())
+def test_batch_independence(backend, make_env):
+    """Environment i's result does not depend on what else is in the batch (no cross-env state)."""
+    m = load_asset("rodent_0")
+    qpos, qvel = make_inputs(m, 4, seed=3)
+    env4 = make_env(backend, synthetic_track(), num_envs=4, model=m, iterations=4, ls_iterations=4)
+    env1 = make_env(backend, synthetic_track(), num_envs=1, model=m, iterations=4, ls_iterations=4)
+    a = env4.debug_forward(torch.tensor(qpos), torch.tensor(qvel))["qacc"].cpu().numpy()
+    b = env1.debug_forward(torch.tensor(qpos[2:3]), torch.tensor(qvel[2:3]))["qacc"].cpu().numpy()
+    assert np.array_equal(a[2], b[0])
