@@ -11,21 +11,51 @@
 #include <cstdio>
 #include <math_constants.h>
 
+/* production kernels: debug-dump / clock64 hooks compiled out */
+#define RR_NS rr
+#define RR_WITH_DEBUG 0
 #include "rr_kernels.inl"
+#undef RR_NS
+#undef RR_WITH_DEBUG
+/* instrumented kernels (parity tests' intermediates, per-phase cycle counts) */
+#define RR_NS rr_dbg
+#define RR_WITH_DEBUG 1
+#include "rr_kernels.inl"
+#undef RR_NS
+#undef RR_WITH_DEBUG
 
-#ifndef RR_WPB
-#define RR_WPB 1
-#endif
+#define RR_MAX_WPB 12
+#define RR_SMEM_MAX 232448 /* 227 KB opt-in dynamic shared memory per CTA on sm_100 */
 
-template <int NS>
-__global__ void __launch_bounds__(32 * RR_WPB) rr_step_kernel(const __grid_constant__ RRModelDev m,
-                                                              const __grid_constant__ RRStepArgs a) {
+/* Persistent CTAs: the model tables (about 29 KB for rodent_0) are staged into shared memory once per CTA, then each
+ * warp loops over its share of the environments. */
+template <int NS, bool DBG>
+__global__ void __launch_bounds__(32 * RR_MAX_WPB, 1) rr_step_kernel(const __grid_constant__ RRModelDev m,
+                                                                     const __grid_constant__ RRStepArgs a) {
   extern __shared__ float4 rr_smem4[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int env = blockIdx.x * RR_WPB + warp;
-  if (env >= a.B) return;
-  float *sm = reinterpret_cast<float *>(rr_smem4) + (size_t)warp * m.sm.total;
-  rr::env_run<NS>(m, a, env, sm, lane);
+  int32_t *ti = reinterpret_cast<int32_t *>(rr_smem4);
+  float *tf = reinterpret_cast<float *>(ti + m.ni);
+  float *envs = tf + m.nf;
+  {
+    int4 *dst = reinterpret_cast<int4 *>(ti);
+    const int4 *src = reinterpret_cast<const int4 *>(m.ibuf);
+    for (int i = threadIdx.x; i < m.ni / 4; i += blockDim.x) dst[i] = __ldg(src + i);
+    float4 *dstf = reinterpret_cast<float4 *>(tf);
+    const float4 *srcf = reinterpret_cast<const float4 *>(m.fbuf);
+    for (int i = threadIdx.x; i < m.nf / 4; i += blockDim.x) dstf[i] = __ldg(srcf + i);
+  }
+  __syncthreads();
+  const int wpb = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float *sm = envs + (size_t)warp * m.sm.total;
+  /* every warp of every CTA runs the same number of passes (the kernel rendezvous CTA-wide for instruction-cache
+   * locality); passes beyond the batch are padding: they recompute the last environment and store nothing */
+  const int stride = gridDim.x * wpb, trips = (a.B + stride - 1) / stride;
+  for (int it = 0; it < trips; it++) {
+    const int env = it * stride + blockIdx.x * wpb + warp;
+    if (DBG) rr_dbg::env_run<NS>(m, a, env, blockIdx.x * wpb + warp, sm, ti, tf, lane);
+    else rr::env_run<NS>(m, a, env, blockIdx.x * wpb + warp, sm, ti, tf, lane);
+    __syncwarp();
+  }
 }
 
 /* ppo.losses.compute_gae: one thread per environment, reverse scan over the unroll (T = 10 in the reference). */
@@ -65,27 +95,46 @@ static int rrb_h2d(void *dst, const void *src, size_t bytes, void *stream) {
 static int rrb_d2h(void *dst, const void *src, size_t bytes, void *stream) {
   return rrb_check(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream), "cudaMemcpyAsync D2H");
 }
+static int rrb_num_slots() {
+  int dev = 0, n_sm = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  return (n_sm > 0 ? n_sm : 160) * RR_MAX_WPB;
+}
 static int rrb_sync(void *stream) { return rrb_check(cudaStreamSynchronize((cudaStream_t)stream), "cudaStreamSynchronize"); }
 
-template <int NS>
+template <int NS, bool DBG>
 static int rrb_launch_ns(const RRModelDev &m, const RRStepArgs &a, void *stream) {
-  size_t smem = (size_t)m.sm.total * sizeof(float) * RR_WPB;
-  static thread_local size_t configured = 0;
-  if (smem > configured) {
-    if (rrb_check(cudaFuncSetAttribute(rr_step_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+  const size_t tables = ((size_t)m.ni + m.nf) * 4, per_env = (size_t)m.sm.total * sizeof(float);
+  if (tables + per_env > RR_SMEM_MAX) {
+    snprintf(g_cuda_err, sizeof(g_cuda_err), "model needs %zu B of shared memory per environment (+%zu B tables) > %d", per_env,
+             tables, RR_SMEM_MAX);
+    return 1;
+  }
+  int wpb = (int)((RR_SMEM_MAX - tables) / per_env);
+  if (wpb > RR_MAX_WPB) wpb = RR_MAX_WPB;
+  size_t smem = tables + per_env * wpb;
+  static thread_local int n_sm = 0;
+  static thread_local bool configured = false;
+  if (!configured) {
+    int dev = 0;
+    if (rrb_check(cudaGetDevice(&dev), "cudaGetDevice") ||
+        rrb_check(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev), "cudaDeviceGetAttribute") ||
+        rrb_check(cudaFuncSetAttribute(rr_step_kernel<NS, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, RR_SMEM_MAX),
                   "cudaFuncSetAttribute(smem)"))
       return 1;
-    cudaFuncSetAttribute(rr_step_kernel<NS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    configured = smem;
+    configured = true;
   }
-  int grid = (a.B + RR_WPB - 1) / RR_WPB;
-  rr_step_kernel<NS><<<grid, 32 * RR_WPB, smem, (cudaStream_t)stream>>>(m, a);
+  int grid = (a.B + wpb - 1) / wpb;
+  if (grid > n_sm) grid = n_sm;
+  rr_step_kernel<NS, DBG><<<grid, 32 * wpb, smem, (cudaStream_t)stream>>>(m, a);
   return rrb_check(cudaGetLastError(), "rr_step_kernel launch");
 }
 
 static int rrb_launch_step(const RRModelDev &m, const RRStepArgs &a, void *stream) {
-  if (m.nv <= 96) return rrb_launch_ns<3>(m, a, stream);
-  return rrb_launch_ns<5>(m, a, stream);
+  const bool dbg = a.dbg.buf != nullptr || a.prof != nullptr;
+  if (m.nv <= 96) return dbg ? rrb_launch_ns<3, true>(m, a, stream) : rrb_launch_ns<3, false>(m, a, stream);
+  return dbg ? rrb_launch_ns<5, true>(m, a, stream) : rrb_launch_ns<5, false>(m, a, stream);
 }
 
 static int rrb_launch_gae(const float *rewards, const float *values, const float *bootstrap, const float *termination,

@@ -7,6 +7,7 @@
  *   int  rrb_h2d(void *dst, const void *src, size_t bytes, void *stream);
  *   int  rrb_d2h(void *dst, const void *src, size_t bytes, void *stream);
  *   int  rrb_sync(void *stream);
+ *   int  rrb_num_slots();                      (upper bound on concurrently resident warps = scratch slots)
  *   int  rrb_launch_step(const RRModelDev &m, const RRStepArgs &a, void *stream);
  *   int  rrb_launch_gae(...);
  *   const char *rrb_error();
@@ -38,6 +39,8 @@ struct rr_env {
   float *d_dbg;
   long long *d_prof;
   float *d_action_stage; /* [B, nu] staging for the host-buffer entry point */
+  float *d_scratch;      /* [warp slots, scratch_stride] overflow for contact Jacobians / constraint rows */
+  int scratch_stride;
 };
 
 static int rr_fail(int code, const std::string &msg) {
@@ -152,12 +155,19 @@ extern "C" int rr_env_create(const rr_model *cm, int32_t num_envs, int32_t devic
     delete e;
     return rr_fail(RR_ECUDA, rrb_error());
   }
+  e->scratch_stride = ((m->dev.nJ + 3) & ~3) + 5 * ((m->dev.nefc + 3) & ~3) + 4;
+  if (rrb_malloc((void **)&e->d_scratch, (size_t)rrb_num_slots() * e->scratch_stride * sizeof(float))) {
+    rrb_free(e->d_action_stage);
+    delete e;
+    return rr_fail(RR_ECUDA, rrb_error());
+  }
   *out = e;
   return RR_OK;
 }
 
 extern "C" void rr_env_destroy(rr_env *e) {
   if (!e) return;
+  if (e->d_scratch) rrb_free(e->d_scratch);
   if (e->d_track) rrb_free(e->d_track);
   if (e->d_action_stage) rrb_free(e->d_action_stage);
   delete e;
@@ -232,6 +242,8 @@ static int rr_fill_args(rr_env *e, const rr_buffers *b, const float *action, int
   a.dbg.buf = e->d_dbg;
   a.dbg.stride = rr_debug_stride_of(e->model->dev);
   a.prof = e->d_prof;
+  a.scratch = e->d_scratch;
+  a.scratch_stride = e->scratch_stride;
   return RR_OK;
 }
 

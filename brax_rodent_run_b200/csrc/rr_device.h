@@ -16,7 +16,7 @@
 #define RR_DEV_INT_TABLES(X)                                                                              \
   X(body_parentid) X(body_rootslot) X(body_jntadr) X(body_jntnum) X(level_adr) X(level_body)              \
   X(jnt_type) X(jnt_qposadr) X(jnt_dofadr) X(jnt_bodyid)                                                  \
-  X(dof_bodyid) X(dof_depth) X(dof_ndesc) X(dof_rowadr) X(M_rowid) X(M_colind)                            \
+  X(dof_bodyid) X(dof_depth) X(dof_ndesc) X(dof_rowadr) X(M_meta)                            \
   X(act_dofadr) X(act_qposadr) X(act_dyntype) X(act_gaintype) X(act_biastype) X(act_ctrllimited)          \
   X(act_forcelimited) X(act_actadr)                                                                       \
   X(pair_fn) X(pair_body) X(pair_conadr) X(pair_lastdof) X(con_pair) X(con_Jadr)                          \
@@ -31,25 +31,22 @@
   X(pair_solimp) X(pair_margin) X(pair_invweight)                                                         \
   X(limit_range) X(limit_margin) X(limit_solref) X(limit_solimp) X(limit_invweight)
 
-/* per-environment shared-memory layout (offsets in floats from the warp's base) */
+/* per-environment shared-memory layout (offsets in floats from the warp's base).  Three regions:
+ *   A persistent state; B mass matrix + factor; C a union recycled by phase:
+ *     C1 kinematics .. smooth forces : xpos xquat cinert cdof | qfrc_act cvel cacc cfrc  (crb fcrb overlay cvel..cfrc)
+ *     C2 collision .. solver         : xpos xquat cdof stay (collision / Jacobians read them); the contact arrays,
+ *                                      Jacobian blocks (capJ floats) and constraint rows (capR rows) overlay
+ *                                      cinert / qfrc_act / cvel / cacc / cfrc, which are dead by then (their
+ *                                      observation slices are written to HBM before the solver in the last substep).
+ */
 struct RRSmem {
-  int qpos, qvel, act, ctrl, actdot;      /* state */
-  int xpos, xquat;                        /* body frames (nbody x 3 / 4) */
-  int com;                                /* nroot x 3 subtree COM of each kinematic tree */
-  int cinert, cdof, cvel;                 /* nbody x 10, nv x 6, nbody x 6 */
-  int M, LD, Dinv;                        /* tree-sparse mass matrix, its LDL' factor, 1/D */
-  int vbuf;                               /* nv staging buffer for mat-vec inputs */
-  int qfrc_act;                           /* nv qfrc_actuator (observation term) */
-  int tmp;                                /* phase-local scratch (see sizes below) */
-  /* aliases inside tmp: */
-  int crb, fcrb;                          /* mass-matrix phase: nbody x 10, nv x 6 */
-  int cacc, cfrc;                         /* rne phase: nbody x 6 each */
-  int con_dist, con_pos, con_frame;       /* constraint phase: ncon, 3 ncon, 9 ncon */
-  int con_J;                              /* 3 x chain per contact, static offsets con_Jadr */
-  int row_D, row_aref, row_Jaref, row_jv; /* nefc each (compact active rows) */
-  int row_id;                             /* nefc ints: limit l -> l ; contact c, k -> nlimit + 4 c + k */
-  int cact;                               /* ncon ints: compact list of active contacts */
-  int total;                              /* floats per environment */
+  int qpos, qvel, act, ctrl, actdot, com, vbuf, Dinv, xq1; /* A */
+  int M, LD;                                               /* B */
+  int xpos, xquat, cdof;                                   /* C, live through the Jacobian build */
+  int cinert, qfrc_act, cvel, cacc, cfrc, crb, fcrb;       /* C1 */
+  int con_dist, con_pos, con_frame, cact, cmeta, con_J, row_D; /* C2 (rows: D aref Jaref jv id, capR each, from row_D) */
+  int capJ, capR;
+  int total; /* floats per environment */
 };
 
 struct RRModelDev {
@@ -57,10 +54,13 @@ struct RRModelDev {
   int solver, iterations, ls_iterations;
   float timestep, gravity[3], tolerance, ls_tolerance, impratio, meaninertia;
   RRSmem sm;
-#define RR__X(n) const int32_t *n;
+  /* The tables live in two contiguous device buffers; the kernel stages both into shared memory once per CTA and
+   * indexes them through the element offsets o_<table> below (RI / RF macros in rr_kernels.inl). */
+  const int32_t *ibuf;
+  const float *fbuf;
+  int ni, nf; /* element counts of ibuf / fbuf (multiples of 4) */
+#define RR__X(n) int o_##n;
   RR_DEV_INT_TABLES(RR__X)
-#undef RR__X
-#define RR__X(n) const float *n;
   RR_DEV_FLOAT_TABLES(RR__X)
 #undef RR__X
 };
@@ -99,6 +99,8 @@ struct RRStepArgs {
   float *xpos, *xquat, *subtree_com, *qfrc_actuator, *cinert, *cvel, *contact_dist, *qacc;
   int *niter; /* [B] solver iterations executed in the last substep */
   RRDebug dbg;
+  float *scratch;     /* [warp slots, scratch_stride] global overflow for contact Jacobians / constraint rows */
+  int scratch_stride; /* floats: align4(nJ) + 5 nefc */
   long long *prof; /* [B, RR_NPROF] clock64 deltas or null */
 };
 

@@ -14,8 +14,14 @@
  * __ballot_sync / __syncwarp / __ldg so that tests/emu can compile the same text for the host and run the
  * 32 lanes as fibers (test infrastructure only -- never a product path).
  */
-#ifndef RR_KERNELS_INL_
-#define RR_KERNELS_INL_
+/* This file may be included more than once with different (RR_NS, RR_WITH_DEBUG): the production kernels are compiled
+ * with the debug-dump / profiling hooks removed (they double the code size and the kernel is instruction-cache bound). */
+#ifndef RR_NS
+#define RR_NS rr
+#endif
+#ifndef RR_WITH_DEBUG
+#define RR_WITH_DEBUG 1
+#endif
 
 #include "../../include/rr_model_fields.h"
 #include "rr_device.h"
@@ -24,8 +30,23 @@
 #define RR_DEV __device__ __forceinline__
 #define RR_HOSTDEV __host__ __device__ inline
 #define RR_DEV_MEMBER __device__ __forceinline__
-#define RR_LDG(p) __ldg(p)
+#define RR_DEV_NOINLINE __device__ __noinline__
 #define RR_CLOCK() clock64()
+#endif
+
+/* model tables staged in shared memory: element `idx` of int / float table `name` */
+#define RI(name, idx) (c.ti[c.m.o_##name + (idx)])
+#define RF(name, idx) (c.tf[c.m.o_##name + (idx)])
+
+/* packed per-entry metadata of the tree-sparse layout: row | col << 8 | rowadr[col] << 16 */
+#define RR_META_ROW(x) ((x) & 255)
+#define RR_META_COL(x) (((x) >> 8) & 255)
+#define RR_META_ANCRADR(x) ((int)((unsigned)(x) >> 16))
+
+/* CTA-wide rendezvous used only to keep the warps of a CTA in the same code region (instruction-cache locality);
+ * it carries no data dependence.  No-op in the host emulator. */
+#ifndef RR_CTA_SYNC
+#define RR_CTA_SYNC() __syncthreads()
 #endif
 
 #define RR_FULL 0xffffffffu
@@ -34,7 +55,7 @@
 #define RR_MAXIMP 0.9999f
 #define RR_SIGN_BIT 0x40000000
 
-namespace rr {
+namespace RR_NS {
 
 RR_DEV float warp_sum(float x) {
 #pragma unroll
@@ -120,7 +141,7 @@ RR_DEV void motion_cross_force(float *r, const float *v, const float *f) {
 RR_DEV float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
 
 /* constraint.py _kbi: stiffness k, damping b and impedance for one row (Appendix B.5) */
-RR_DEV void kbi(float timestep, const float *solref, const float *solimp, float pos, float &k, float &b, float &imp) {
+RR_DEV_NOINLINE void kbi(float timestep, const float *solref, const float *solimp, float pos, float &k, float &b, float &imp) {
   float timeconst = fmaxf(solref[0], 2.f * timestep), dampratio = solref[1];
   float dmin = clampf(solimp[0], RR_MINIMP, RR_MAXIMP), dmax = clampf(solimp[1], RR_MINIMP, RR_MAXIMP);
   float width = fmaxf(solimp[2], RR_MINVAL), mid = clampf(solimp[3], RR_MINIMP, RR_MAXIMP), power = fmaxf(solimp[4], 1.f);
@@ -142,39 +163,63 @@ struct Ctx {
   const RRModelDev &m;
   const RRStepArgs &a;
   int env, lane;
+  const int32_t *ti; /* shared-memory copies of the model tables */
+  const float *tf;
   float *qpos, *qvel, *act, *ctrl, *actdot, *xpos, *xquat, *com, *cinert, *cdof, *cvel, *M, *LD, *Dinv, *vbuf, *qfrc_act;
   float *crb, *fcrb, *cacc, *cfrc, *con_dist, *con_pos, *con_frame, *con_J, *row_D, *row_aref, *row_Jaref, *row_jv;
-  int *row_id, *cact;
+  int *row_id, *cact, *cmeta;
+  float *xq1; /* xquat of body 1 saved for the observation (xquat itself is recycled by the solver phase) */
+  float *sm_base, *gJ, *grows; /* shared-memory base; global overflow for contact Jacobians / rows */
   /* per-lane dof metadata: dof i = lane + 32 s */
   int radr[NS], dep[NS], nd[NS];
   float dinv[NS];
   /* register-resident nv-vectors */
   float qfrc_smooth[NS], qacc_smooth[NS], warm[NS], qacc[NS], qfrc_constraint[NS];
   int nla, nca; /* active limit rows, active contacts; rows = nla + 4 nca */
+  bool live;         /* false: padding pass of a persistent warp (keeps CTA barriers matched); no global stores */
+  bool last_substep; /* the forward pass whose cinert / cvel / qfrc_actuator the observation reports */
   int niter;
   float *dbg;
   long long tprev;
 
-  RR_DEV_MEMBER Ctx(const RRModelDev &m_, const RRStepArgs &a_, int env_, float *sm, int lane_) : m(m_), a(a_), env(env_), lane(lane_) {
+  /* constraint rows live in shared memory when at most capR are active, else in the per-warp global scratch */
+  RR_DEV_MEMBER void use_rows(bool in_smem) {
     const RRSmem &s = m.sm;
+    float *base = in_smem ? sm_base + s.row_D : grows;
+    int stride = in_smem ? s.capR : m.nefc;
+    row_D = base; row_aref = base + stride; row_Jaref = base + 2 * stride; row_jv = base + 3 * stride;
+    row_id = (int *)(base + 4 * stride);
+  }
+
+  RR_DEV_MEMBER Ctx(const RRModelDev &m_, const RRStepArgs &a_, int env_, int slot_, float *sm, const int32_t *ti_, const float *tf_,
+                    int lane_)
+      : m(m_), a(a_), env(env_), lane(lane_), ti(ti_), tf(tf_) {
+    const RRSmem &s = m.sm;
+    sm_base = sm;
+    gJ = a.scratch + (size_t)slot_ * a.scratch_stride;
+    grows = gJ + ((m.nJ + 3) & ~3);
+    cmeta = (int *)(sm + s.cmeta);
+    xq1 = sm + s.xq1;
     qpos = sm + s.qpos; qvel = sm + s.qvel; act = sm + s.act; ctrl = sm + s.ctrl; actdot = sm + s.actdot;
     xpos = sm + s.xpos; xquat = sm + s.xquat; com = sm + s.com; cinert = sm + s.cinert; cdof = sm + s.cdof;
     cvel = sm + s.cvel; M = sm + s.M; LD = sm + s.LD; Dinv = sm + s.Dinv; vbuf = sm + s.vbuf; qfrc_act = sm + s.qfrc_act;
     crb = sm + s.crb; fcrb = sm + s.fcrb; cacc = sm + s.cacc; cfrc = sm + s.cfrc;
     con_dist = sm + s.con_dist; con_pos = sm + s.con_pos; con_frame = sm + s.con_frame; con_J = sm + s.con_J;
-    row_D = sm + s.row_D; row_aref = sm + s.row_aref; row_Jaref = sm + s.row_Jaref; row_jv = sm + s.row_jv;
-    row_id = (int *)(sm + s.row_id); cact = (int *)(sm + s.cact);
+    cact = (int *)(sm + s.cact);
+    use_rows(true);
 #pragma unroll
     for (int s_ = 0; s_ < NS; s_++) {
       int i = lane + 32 * s_;
       bool v = i < m.nv;
-      radr[s_] = v ? RR_LDG(&m.dof_rowadr[i]) : 0;
-      dep[s_] = v ? RR_LDG(&m.dof_depth[i]) : 0;
-      nd[s_] = v ? RR_LDG(&m.dof_ndesc[i]) : 0;
+      radr[s_] = v ? ti[m.o_dof_rowadr + i] : 0;
+      dep[s_] = v ? ti[m.o_dof_depth + i] : 0;
+      nd[s_] = v ? ti[m.o_dof_ndesc + i] : 0;
       dinv[s_] = 0.f;
     }
     nla = nca = 0;
     niter = 0;
+    last_substep = false;
+    live = true;
     dbg = a.dbg.buf ? a.dbg.buf + (size_t)env * a.dbg.stride : nullptr;
     tprev = 0;
   }
@@ -184,7 +229,7 @@ struct Ctx {
 
 template <int NS>
 RR_DEV void prof(Ctx<NS> &c, int id) {
-  if (c.a.prof) {
+  if (RR_WITH_DEBUG && c.a.prof && c.live) {
     long long t = RR_CLOCK();
     if (c.lane == 0) c.a.prof[(size_t)c.env * RR_NPROF + id] += t - c.tprev;
     c.tprev = t;
@@ -246,13 +291,13 @@ RR_HOSTDEV int dbg_offset(const RRModelDev &m, int f) {
 }
 template <int NS>
 RR_DEV void dbg_copy(Ctx<NS> &c, int field, const float *src, int n) {
-  if (!c.dbg) return;
+  if (!RR_WITH_DEBUG || !c.dbg) return;
   float *dst = c.dbg + dbg_offset(c.m, field);
   for (int i = c.lane; i < n; i += 32) dst[i] = src[i];
 }
 template <int NS>
 RR_DEV void dbg_vec(Ctx<NS> &c, int field, const float (&x)[NS]) {
-  if (!c.dbg) return;
+  if (!RR_WITH_DEBUG || !c.dbg) return;
   float *dst = c.dbg + dbg_offset(c.m, field);
   RR_FOR_S { int i = c.lane + 32 * s; if (i < c.m.nv) dst[i] = x[s]; }
 }
@@ -268,23 +313,23 @@ RR_DEV void kinematics(Ctx<NS> &c) {
   }
   __syncwarp();
   for (int lev = 1; lev < m.nlevel; lev++) {
-    int beg = RR_LDG(&m.level_adr[lev]), end = RR_LDG(&m.level_adr[lev + 1]);
+    int beg = RI(level_adr, lev), end = RI(level_adr, lev + 1);
     for (int idx = beg + c.lane; idx < end; idx += 32) {
-      int b = RR_LDG(&m.level_body[idx]);
-      int p = RR_LDG(&m.body_parentid[b]);
+      int b = RI(level_body, idx);
+      int p = RI(body_parentid, b);
       float ppos[3], pquat[4], bp[3], bq[4], pos[3], quat[4], r[3];
 #pragma unroll
-      for (int k = 0; k < 3; k++) { ppos[k] = c.xpos[3 * p + k]; bp[k] = RR_LDG(&m.body_pos[3 * b + k]); }
+      for (int k = 0; k < 3; k++) { ppos[k] = c.xpos[3 * p + k]; bp[k] = RF(body_pos, 3 * b + k); }
 #pragma unroll
-      for (int k = 0; k < 4; k++) { pquat[k] = c.xquat[4 * p + k]; bq[k] = RR_LDG(&m.body_quat[4 * b + k]); }
+      for (int k = 0; k < 4; k++) { pquat[k] = c.xquat[4 * p + k]; bq[k] = RF(body_quat, 4 * b + k); }
       rotq(r, bp, pquat);
 #pragma unroll
       for (int k = 0; k < 3; k++) pos[k] = ppos[k] + r[k];
       quat_mul(quat, pquat, bq);
-      int jadr = RR_LDG(&m.body_jntadr[b]), jnum = RR_LDG(&m.body_jntnum[b]);
+      int jadr = RI(body_jntadr, b), jnum = RI(body_jntnum, b);
       for (int j = jadr; j < jadr + jnum; j++) {
-        int qa = RR_LDG(&m.jnt_qposadr[j]), da = RR_LDG(&m.jnt_dofadr[j]);
-        if (RR_LDG(&m.jnt_type[j]) == RR_JNT_FREE) {
+        int qa = RI(jnt_qposadr, j), da = RI(jnt_dofadr, j);
+        if (RI(jnt_type, j) == RR_JNT_FREE) {
 #pragma unroll
           for (int k = 0; k < 3; k++) pos[k] = c.qpos[qa + k];
 #pragma unroll
@@ -295,12 +340,12 @@ RR_DEV void kinematics(Ctx<NS> &c) {
         } else {
           float jp[3], ja[3], anchor[3], axis[3], qloc[4], q2[4];
 #pragma unroll
-          for (int k = 0; k < 3; k++) { jp[k] = RR_LDG(&m.jnt_pos[3 * j + k]); ja[k] = RR_LDG(&m.jnt_axis[3 * j + k]); }
+          for (int k = 0; k < 3; k++) { jp[k] = RF(jnt_pos, 3 * j + k); ja[k] = RF(jnt_axis, 3 * j + k); }
           rotq(r, jp, quat);
 #pragma unroll
           for (int k = 0; k < 3; k++) anchor[k] = r[k] + pos[k];
           rotq(axis, ja, quat);
-          axis_angle_quat(qloc, ja, c.qpos[qa] - RR_LDG(&m.qpos0[qa]));
+          axis_angle_quat(qloc, ja, c.qpos[qa] - RF(qpos0, qa));
           quat_mul(q2, quat, qloc);
 #pragma unroll
           for (int k = 0; k < 4; k++) quat[k] = q2[k];
@@ -315,7 +360,7 @@ RR_DEV void kinematics(Ctx<NS> &c) {
       }
       float ip[3];
 #pragma unroll
-      for (int k = 0; k < 3; k++) { c.xpos[3 * b + k] = pos[k]; ip[k] = RR_LDG(&m.body_ipos[3 * b + k]); }
+      for (int k = 0; k < 3; k++) { c.xpos[3 * b + k] = pos[k]; ip[k] = RF(body_ipos, 3 * b + k); }
 #pragma unroll
       for (int k = 0; k < 4; k++) c.xquat[4 * b + k] = quat[k];
       rotq(r, ip, quat);
@@ -333,8 +378,8 @@ RR_DEV void com_pos(Ctx<NS> &c) {
   for (int r = 0; r < m.nroot; r++) {
     float sx = 0.f, sy = 0.f, sz = 0.f, sm = 0.f;
     for (int b = 1 + c.lane; b < m.nbody; b += 32) {
-      if (RR_LDG(&m.body_rootslot[b]) == r) {
-        float mass = RR_LDG(&m.body_mass[b]);
+      if (RI(body_rootslot, b) == r) {
+        float mass = RF(body_mass, b);
         sx += c.cinert[10 * b + 6] * mass; sy += c.cinert[10 * b + 7] * mass; sz += c.cinert[10 * b + 8] * mass;
         sm += mass;
       }
@@ -358,13 +403,13 @@ RR_DEV void com_pos(Ctx<NS> &c) {
     }
     float q[4], iq[4], xq[4], R[9], I[3], off[3];
 #pragma unroll
-    for (int k = 0; k < 4; k++) { xq[k] = c.xquat[4 * b + k]; iq[k] = RR_LDG(&m.body_iquat[4 * b + k]); }
+    for (int k = 0; k < 4; k++) { xq[k] = c.xquat[4 * b + k]; iq[k] = RF(body_iquat, 4 * b + k); }
     quat_mul(q, xq, iq);
     quat_to_mat(R, q);
-    int rs = RR_LDG(&m.body_rootslot[b]);
-    float mb = RR_LDG(&m.body_mass[b]);
+    int rs = RI(body_rootslot, b);
+    float mb = RF(body_mass, b);
 #pragma unroll
-    for (int k = 0; k < 3; k++) { I[k] = RR_LDG(&m.body_inertia[3 * b + k]); off[k] = ci[6 + k] - c.com[3 * rs + k]; }
+    for (int k = 0; k < 3; k++) { I[k] = RF(body_inertia, 3 * b + k); off[k] = ci[6 + k] - c.com[3 * rs + k]; }
     float d2 = dot3(off, off);
     float A00 = R[0] * I[0] * R[0] + R[1] * I[1] * R[1] + R[2] * I[2] * R[2] + mb * (d2 - off[0] * off[0]);
     float A11 = R[3] * I[0] * R[3] + R[4] * I[1] * R[4] + R[5] * I[2] * R[5] + mb * (d2 - off[1] * off[1]);
@@ -377,10 +422,10 @@ RR_DEV void com_pos(Ctx<NS> &c) {
   }
   /* cdof: [ang; lin] about the tree COM */
   for (int j = c.lane; j < m.njnt; j += 32) {
-    int b = RR_LDG(&m.jnt_bodyid[j]), da = RR_LDG(&m.jnt_dofadr[j]);
-    int rs = RR_LDG(&m.body_rootslot[b]);
+    int b = RI(jnt_bodyid, j), da = RI(jnt_dofadr, j);
+    int rs = RI(body_rootslot, b);
     float *cd = c.cdof + 6 * da;
-    if (RR_LDG(&m.jnt_type[j]) == RR_JNT_FREE) {
+    if (RI(jnt_type, j) == RR_JNT_FREE) {
       float R[9], xq[4], off[3];
 #pragma unroll
       for (int k = 0; k < 4; k++) xq[k] = c.xquat[4 * b + k];
@@ -415,86 +460,127 @@ RR_DEV void crb_and_mass_matrix(Ctx<NS> &c) {
   for (int i = c.lane; i < 10 * m.nbody; i += 32) c.crb[i] = c.cinert[i];
   __syncwarp();
   for (int b = m.nbody - 1; b > 0; b--) {
-    int p = RR_LDG(&m.body_parentid[b]);
+    int p = RI(body_parentid, b);
     if (c.lane < 10 && p > 0) c.crb[10 * p + c.lane] += c.crb[10 * b + c.lane];
     __syncwarp();
   }
-  for (int i = c.lane; i < m.nv; i += 32) {
-    float f[6], cr[10], cd[6];
-    int b = RR_LDG(&m.dof_bodyid[i]);
+  /* row i of qM: f = crb[body(i)] * cdof[i], then M(i, a) = cdof[a] . f for every ancestor-or-self a of i */
+  RR_FOR_S {
+    int i = c.lane + 32 * s;
+    if (i < m.nv) {
+      float f[6], cr[10], cd[6];
+      int b = RI(dof_bodyid, i);
 #pragma unroll
-    for (int k = 0; k < 10; k++) cr[k] = c.crb[10 * b + k];
+      for (int k = 0; k < 10; k++) cr[k] = c.crb[10 * b + k];
 #pragma unroll
-    for (int k = 0; k < 6; k++) cd[k] = c.cdof[6 * i + k];
-    inert_mul(f, cr, cd);
-#pragma unroll
-    for (int k = 0; k < 6; k++) c.fcrb[6 * i + k] = f[k];
-  }
-  __syncwarp();
-  for (int e = c.lane; e < m.nM; e += 32) {
-    int i = RR_LDG(&m.M_rowid[e]), j = RR_LDG(&m.M_colind[e]);
-    float v = 0.f;
-#pragma unroll
-    for (int k = 0; k < 6; k++) v += c.cdof[6 * j + k] * c.fcrb[6 * i + k];
-    if (i == j) v += RR_LDG(&m.dof_armature[i]);
-    c.M[e] = v;
+      for (int k = 0; k < 6; k++) cd[k] = c.cdof[6 * i + k];
+      inert_mul(f, cr, cd);
+      const int adr = c.radr[s], dp = c.dep[s];
+      for (int t = 0; t <= dp; t++) {
+        const float *cj = c.cdof + 6 * RR_META_COL(RI(M_meta, adr + t));
+        float v = cj[0] * f[0] + cj[1] * f[1] + cj[2] * f[2] + cj[3] * f[3] + cj[4] * f[4] + cj[5] * f[5];
+        if (t == dp) v += RF(dof_armature, i);
+        c.M[adr + t] = v;
+      }
+    }
   }
   __syncwarp();
 }
 
-/* Tree-sparse LDL' of (M + diag_add) into LD / Dinv (MuJoCo mj_factorM order: leaves to root).  Equivalent to the
- * dense Cholesky MJX runs (jax.scipy cho_factor) up to rounding. */
+/* Tree-sparse L'DL factorisation of (M + diag_scale * damping) into LD / Dinv (the factorisation MuJoCo's
+ * mj_factorM computes, leaves to root; equivalent to the dense Cholesky MJX runs, jax.scipy cho_factor, up to
+ * rounding).  Gather form: row k is final once the rows of all its descendants j are,
+ *   row_k[s] = M(k, a_s) - sum_j L(j, k) D_j L(j, a_s),   D_k = row_k[diag],   L(k, a_s) = row_k[s] / D_k,
+ * with lane s accumulating entry s in a register (rows deeper than 32 take a second register) and the per-descendant
+ * scalars w_j = L(j, k) D_j staged through vbuf. */
 template <int NS>
 RR_DEV void factor(Ctx<NS> &c, float diag_scale) {
   const RRModelDev &m = c.m;
-  for (int e = c.lane; e < m.nM; e += 32) {
-    float v = c.M[e];
-    int i = RR_LDG(&m.M_rowid[e]);
-    if (diag_scale != 0.f && i == RR_LDG(&m.M_colind[e])) v += diag_scale * RR_LDG(&m.dof_damping[i]);
-    c.LD[e] = v;
-  }
   __syncwarp();
-  for (int k = m.nv - 1; k > 0; k--) {
-    int mk = RR_LDG(&m.dof_depth[k]);
-    if (mk == 0) continue;
-    int adr = RR_LDG(&m.dof_rowadr[k]);
-    float dk = c.LD[adr + mk];
-    for (int t = c.lane; t < mk; t += 32) {
-      int i = RR_LDG(&m.M_colind[adr + t]);
-      int ra = RR_LDG(&m.dof_rowadr[i]);
-      float tmp = c.LD[adr + t] / dk;
-      for (int s = 0; s <= t; s++) c.LD[ra + s] -= c.LD[adr + s] * tmp;
+#pragma unroll 1
+  for (int k = m.nv - 1; k >= 0; k--) {
+    const int mk = RI(dof_depth, k), adr = RI(dof_rowadr, k), nd = RI(dof_ndesc, k);
+    const int s0 = c.lane, s1 = c.lane + 32;
+    float acc0 = 0.f, acc1 = 0.f;
+    if (s0 <= mk) acc0 = c.M[adr + s0];
+    if (s1 <= mk) acc1 = c.M[adr + s1];
+    if (diag_scale != 0.f) {
+      float dd = diag_scale * RF(dof_damping, k);
+      if (s0 == mk) acc0 += dd;
+      if (s1 == mk) acc1 += dd;
     }
-    __syncwarp();
-    for (int t = c.lane; t < mk; t += 32) c.LD[adr + t] = c.LD[adr + t] / dk;
+    if (nd > 0) {
+      for (int jj = c.lane; jj < nd; jj += 32) {
+        int j = k + 1 + jj, rj = RI(dof_rowadr, j);
+        c.vbuf[jj] = c.LD[rj + mk] * c.LD[rj + RI(dof_depth, j)];
+      }
+      __syncwarp();
+      if (mk < 32) {
+#pragma unroll 4
+        for (int jj = 0; jj < nd; jj++) {
+          const int rj = RI(dof_rowadr, k + 1 + jj);
+          const float w = c.vbuf[jj];
+          if (s0 <= mk) acc0 -= w * c.LD[rj + s0];
+        }
+      } else {
+#pragma unroll 2
+        for (int jj = 0; jj < nd; jj++) {
+          const int rj = RI(dof_rowadr, k + 1 + jj);
+          const float w = c.vbuf[jj];
+          acc0 -= w * c.LD[rj + s0];
+          if (s1 <= mk) acc1 -= w * c.LD[rj + s1];
+        }
+      }
+    }
+    /* D_k sits in lane mk (or mk - 32 of the second register) */
+    const float dk = __shfl_sync(RR_FULL, mk < 32 ? acc0 : acc1, mk & 31);
+    const float inv = 1.f / dk;
+    if (s0 < mk) c.LD[adr + s0] = acc0 * inv;
+    if (s1 < mk) c.LD[adr + s1] = acc1 * inv;
+    if (c.lane == 0) { c.LD[adr + mk] = dk; c.Dinv[k] = inv; }
     __syncwarp();
   }
-  for (int i = c.lane; i < m.nv; i += 32) c.Dinv[i] = 1.f / c.LD[RR_LDG(&m.dof_rowadr[i]) + RR_LDG(&m.dof_depth[i])];
-  __syncwarp();
   RR_FOR_S { int i = c.lane + 32 * s; c.dinv[s] = i < m.nv ? c.Dinv[i] : 0.f; }
 }
 
-/* x <- (L D L')^-1 x with x distributed over lanes (dof i = lane + 32 s); pure register / shuffle solve. */
+/* x <- (L D L')^-1 x with x distributed over lanes (dof i = lane + 32 s); pure register / shuffle solve.
+ * Per step one value and its row metadata are broadcast from the owning lane; L(i, j) sits at rowadr[i] + depth[j]. */
 template <int NS>
 RR_DEV void solve_ld(Ctx<NS> &c, float (&x)[NS]) {
-  const RRModelDev &m = c.m;
-  for (int i = m.nv - 1; i > 0; i--) {
-    float xi = __shfl_sync(RR_FULL, vselect<NS>(x, i >> 5), i & 31);
-    int adr = RR_LDG(&m.dof_rowadr[i]);
-    RR_FOR_S {
-      int j = c.lane + 32 * s;
-      if (j < i && i <= j + c.nd[s]) x[s] -= c.LD[adr + c.dep[s]] * xi;
+  const int nv = c.m.nv;
+  /* backward: x <- L^-T x, leaves to root */
+#pragma unroll
+  for (int si = NS - 1; si >= 0; si--) {
+    const int top = (nv - 32 * si) < 32 ? (nv - 32 * si) : 32;
+    for (int src = top - 1; src >= 0; src--) {
+      const int i = 32 * si + src;
+      const int depi = __shfl_sync(RR_FULL, c.dep[si], src);
+      if (depi == 0) continue;
+      const float xi = __shfl_sync(RR_FULL, x[si], src);
+      const int adr = __shfl_sync(RR_FULL, c.radr[si], src);
+#pragma unroll
+      for (int s = 0; s <= si; s++) {
+        const int j = c.lane + 32 * s;
+        if (j < i && i <= j + c.nd[s]) x[s] -= c.LD[adr + c.dep[s]] * xi;
+      }
     }
   }
   RR_FOR_S x[s] *= c.dinv[s];
-  for (int j = 0; j < m.nv - 1; j++) {
-    int ndj = RR_LDG(&m.dof_ndesc[j]);
-    if (ndj == 0) continue;
-    float xj = __shfl_sync(RR_FULL, vselect<NS>(x, j >> 5), j & 31);
-    int depj = RR_LDG(&m.dof_depth[j]);
-    RR_FOR_S {
-      int i = c.lane + 32 * s;
-      if (i > j && i <= j + ndj) x[s] -= c.LD[c.radr[s] + depj] * xj;
+  /* forward: x <- L^-1 x, root to leaves */
+#pragma unroll
+  for (int sj = 0; sj < NS; sj++) {
+    const int top = (nv - 32 * sj) < 32 ? (nv - 32 * sj) : 32;
+    for (int src = 0; src < top; src++) {
+      const int j = 32 * sj + src;
+      const int ndj = __shfl_sync(RR_FULL, c.nd[sj], src);
+      if (ndj == 0) continue;
+      const float xj = __shfl_sync(RR_FULL, x[sj], src);
+      const int depj = __shfl_sync(RR_FULL, c.dep[sj], src);
+#pragma unroll
+      for (int s = sj; s < NS; s++) {
+        const int i = c.lane + 32 * s;
+        if (i > j && i <= j + ndj) x[s] -= c.LD[c.radr[s] + depj] * xj;
+      }
     }
   }
 }
@@ -511,8 +597,10 @@ RR_DEV void mul_m(Ctx<NS> &c, float (&y)[NS], const float (&v)[NS]) {
     float acc = 0.f;
     if (i < m.nv) {
       int adr = c.radr[s];
-      for (int t = 0; t <= c.dep[s]; t++) acc += c.M[adr + t] * c.vbuf[RR_LDG(&m.M_colind[adr + t])];
-      for (int k = i + 1; k <= i + c.nd[s]; k++) acc += c.M[RR_LDG(&m.dof_rowadr[k]) + c.dep[s]] * c.vbuf[k];
+#pragma unroll 2
+      for (int t = 0; t <= c.dep[s]; t++) acc += c.M[adr + t] * c.vbuf[RR_META_COL(RI(M_meta, adr + t))];
+#pragma unroll 2
+      for (int k = i + 1; k <= i + c.nd[s]; k++) acc += c.M[RI(dof_rowadr, k) + c.dep[s]] * c.vbuf[k];
     }
     y[s] = acc;
   }
@@ -529,17 +617,17 @@ RR_DEV void com_vel_and_rne(Ctx<NS> &c, float (&qfrc_bias)[NS]) {
   }
   __syncwarp();
   for (int lev = 1; lev < m.nlevel; lev++) {
-    int beg = RR_LDG(&m.level_adr[lev]), end = RR_LDG(&m.level_adr[lev + 1]);
+    int beg = RI(level_adr, lev), end = RI(level_adr, lev + 1);
     for (int idx = beg + c.lane; idx < end; idx += 32) {
-      int b = RR_LDG(&m.level_body[idx]);
-      int p = RR_LDG(&m.body_parentid[b]);
+      int b = RI(level_body, idx);
+      int p = RI(body_parentid, b);
       float cv[6], ca[6];
 #pragma unroll
       for (int k = 0; k < 6; k++) { cv[k] = c.cvel[6 * p + k]; ca[k] = c.cacc[6 * p + k]; }
-      int jadr = RR_LDG(&m.body_jntadr[b]), jnum = RR_LDG(&m.body_jntnum[b]);
+      int jadr = RI(body_jntadr, b), jnum = RI(body_jntnum, b);
       for (int j = jadr; j < jadr + jnum; j++) {
-        int d0 = RR_LDG(&m.jnt_dofadr[j]);
-        if (RR_LDG(&m.jnt_type[j]) == RR_JNT_FREE) {
+        int d0 = RI(jnt_dofadr, j);
+        if (RI(jnt_type, j) == RR_JNT_FREE) {
 #pragma unroll
           for (int d = 0; d < 3; d++) {
             float qv = c.qvel[d0 + d];
@@ -585,11 +673,11 @@ RR_DEV void com_vel_and_rne(Ctx<NS> &c, float (&qfrc_bias)[NS]) {
     inert_mul(f2, ci, cv);
     motion_cross_force(f3, cv, f2);
 #pragma unroll
-    for (int k = 0; k < 6; k++) c.cfrc[6 * b + k] = f1[k] + f3[k];
+    for (int k = 0; k < 6; k++) c.cfrc[6 * b + k] = f1[k] + f3[k]; /* cfrc aliases cacc: body-local, in place */
   }
   __syncwarp();
   for (int b = m.nbody - 1; b > 0; b--) {
-    int p = RR_LDG(&m.body_parentid[b]);
+    int p = RI(body_parentid, b);
     if (c.lane < 6 && p > 0) c.cfrc[6 * p + c.lane] += c.cfrc[6 * b + c.lane];
     __syncwarp();
   }
@@ -597,7 +685,7 @@ RR_DEV void com_vel_and_rne(Ctx<NS> &c, float (&qfrc_bias)[NS]) {
     int i = c.lane + 32 * s;
     float v = 0.f;
     if (i < m.nv) {
-      int b = RR_LDG(&m.dof_bodyid[i]);
+      int b = RI(dof_bodyid, i);
 #pragma unroll
       for (int k = 0; k < 6; k++) v += c.cdof[6 * i + k] * c.cfrc[6 * b + k];
     }
@@ -605,7 +693,7 @@ RR_DEV void com_vel_and_rne(Ctx<NS> &c, float (&qfrc_bias)[NS]) {
   }
 }
 
-/* passive + actuation -> qfrc_smooth, qacc_smooth */
+/* passive + actuation -> qfrc_smooth (qacc_smooth = M^-1 qfrc_smooth is solved by the caller) */
 template <int NS>
 RR_DEV void smooth_forces(Ctx<NS> &c, const float (&qfrc_bias)[NS]) {
   const RRModelDev &m = c.m;
@@ -614,37 +702,37 @@ RR_DEV void smooth_forces(Ctx<NS> &c, const float (&qfrc_bias)[NS]) {
   for (int i = c.lane; i < m.nv; i += 32) { c.vbuf[i] = 0.f; c.qfrc_act[i] = 0.f; }
   __syncwarp();
   for (int j = c.lane; j < m.njnt; j += 32) {
-    int qa = RR_LDG(&m.jnt_qposadr[j]), da = RR_LDG(&m.jnt_dofadr[j]);
-    float k = RR_LDG(&m.jnt_stiffness[j]);
-    if (RR_LDG(&m.jnt_type[j]) == RR_JNT_FREE) {
+    int qa = RI(jnt_qposadr, j), da = RI(jnt_dofadr, j);
+    float k = RF(jnt_stiffness, j);
+    if (RI(jnt_type, j) == RR_JNT_FREE) {
       /* free-joint spring: translational part only matters when stiffness != 0 (never for <freejoint>) */
 #pragma unroll
-      for (int d = 0; d < 3; d++) c.vbuf[da + d] = -k * (c.qpos[qa + d] - RR_LDG(&m.qpos_spring[qa + d]));
+      for (int d = 0; d < 3; d++) c.vbuf[da + d] = -k * (c.qpos[qa + d] - RF(qpos_spring, qa + d));
     } else {
-      c.vbuf[da] = -k * (c.qpos[qa] - RR_LDG(&m.qpos_spring[qa]));
+      c.vbuf[da] = -k * (c.qpos[qa] - RF(qpos_spring, qa));
     }
   }
   /* actuation (fwd_actuation): filter activation, affine gain / bias, joint transmission */
   for (int u = c.lane; u < m.nu; u += 32) {
     float ctrl = c.ctrl[u];
-    if (RR_LDG(&m.act_ctrllimited[u])) ctrl = clampf(ctrl, RR_LDG(&m.act_ctrlrange[2 * u]), RR_LDG(&m.act_ctrlrange[2 * u + 1]));
-    int da = RR_LDG(&m.act_dofadr[u]), qa = RR_LDG(&m.act_qposadr[u]);
-    float gear = RR_LDG(&m.act_gear[u]);
+    if (RI(act_ctrllimited, u)) ctrl = clampf(ctrl, RF(act_ctrlrange, 2 * u), RF(act_ctrlrange, 2 * u + 1));
+    int da = RI(act_dofadr, u), qa = RI(act_qposadr, u);
+    float gear = RF(act_gear, u);
     float len = gear * c.qpos[qa], vel = gear * c.qvel[da];
     float ctrl_act = ctrl;
-    if (RR_LDG(&m.act_dyntype[u]) == 2) {
-      int aa = RR_LDG(&m.act_actadr[u]);
-      float tau = fmaxf(RR_LDG(&m.act_dynprm[u]), RR_MINVAL);
+    if (RI(act_dyntype, u) == 2) {
+      int aa = RI(act_actadr, u);
+      float tau = fmaxf(RF(act_dynprm, u), RR_MINVAL);
       c.actdot[aa] = (ctrl - c.act[aa]) / tau;
       ctrl_act = c.act[aa];
     }
-    float gain = RR_LDG(&m.act_gainprm[3 * u]);
-    if (RR_LDG(&m.act_gaintype[u]) == 1) gain += RR_LDG(&m.act_gainprm[3 * u + 1]) * len + RR_LDG(&m.act_gainprm[3 * u + 2]) * vel;
+    float gain = RF(act_gainprm, 3 * u);
+    if (RI(act_gaintype, u) == 1) gain += RF(act_gainprm, 3 * u + 1) * len + RF(act_gainprm, 3 * u + 2) * vel;
     float bias = 0.f;
-    if (RR_LDG(&m.act_biastype[u]) == 1)
-      bias = RR_LDG(&m.act_biasprm[3 * u]) + RR_LDG(&m.act_biasprm[3 * u + 1]) * len + RR_LDG(&m.act_biasprm[3 * u + 2]) * vel;
+    if (RI(act_biastype, u) == 1)
+      bias = RF(act_biasprm, 3 * u) + RF(act_biasprm, 3 * u + 1) * len + RF(act_biasprm, 3 * u + 2) * vel;
     float force = gain * ctrl_act + bias;
-    if (RR_LDG(&m.act_forcelimited[u])) force = clampf(force, RR_LDG(&m.act_forcerange[2 * u]), RR_LDG(&m.act_forcerange[2 * u + 1]));
+    if (RI(act_forcelimited, u)) force = clampf(force, RF(act_forcerange, 2 * u), RF(act_forcerange, 2 * u + 1));
     c.qfrc_act[da] = gear * force;
   }
   __syncwarp();
@@ -652,7 +740,7 @@ RR_DEV void smooth_forces(Ctx<NS> &c, const float (&qfrc_bias)[NS]) {
   RR_FOR_S {
     int i = c.lane + 32 * s;
     float pv = 0.f, av = 0.f;
-    if (i < m.nv) { pv = c.vbuf[i] - RR_LDG(&m.dof_damping[i]) * c.qvel[i]; av = c.qfrc_act[i]; }
+    if (i < m.nv) { pv = c.vbuf[i] - RF(dof_damping, i) * c.qvel[i]; av = c.qfrc_act[i]; }
     passive[s] = pv;
     c.qfrc_smooth[s] = pv - qfrc_bias[s] + av;
     c.qacc_smooth[s] = c.qfrc_smooth[s];
@@ -660,9 +748,7 @@ RR_DEV void smooth_forces(Ctx<NS> &c, const float (&qfrc_bias)[NS]) {
   dbg_vec<NS>(c, RR_DBG_QFRC_BIAS, qfrc_bias);
   dbg_vec<NS>(c, RR_DBG_QFRC_PASSIVE, passive);
   dbg_copy<NS>(c, RR_DBG_QFRC_ACTUATOR, c.qfrc_act, m.nv);
-  solve_ld<NS>(c, c.qacc_smooth);
   dbg_vec<NS>(c, RR_DBG_QFRC_SMOOTH, c.qfrc_smooth);
-  dbg_vec<NS>(c, RR_DBG_QACC_SMOOTH, c.qacc_smooth);
 }
 
 /* ------------------------------------------------------------------------------------------ collision (B.4) */
@@ -684,15 +770,15 @@ template <int NS>
 RR_DEV void collision(Ctx<NS> &c) {
   const RRModelDev &m = c.m;
   for (int p = c.lane; p < m.npair; p += 32) {
-    int b = RR_LDG(&m.pair_body[p]), ca = RR_LDG(&m.pair_conadr[p]), fn = RR_LDG(&m.pair_fn[p]);
+    int b = RI(pair_body, p), ca = RI(pair_conadr, p), fn = RI(pair_fn, p);
     float n[3], pp[3], gl[3], gq[4], xq[4], gp[3], r[3], size[3];
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-      n[k] = RR_LDG(&m.pair_plane_n[3 * p + k]); pp[k] = RR_LDG(&m.pair_plane_p[3 * p + k]);
-      gl[k] = RR_LDG(&m.pair_gpos[3 * p + k]); size[k] = RR_LDG(&m.pair_size[3 * p + k]);
+      n[k] = RF(pair_plane_n, 3 * p + k); pp[k] = RF(pair_plane_p, 3 * p + k);
+      gl[k] = RF(pair_gpos, 3 * p + k); size[k] = RF(pair_size, 3 * p + k);
     }
 #pragma unroll
-    for (int k = 0; k < 4; k++) { xq[k] = c.xquat[4 * b + k]; gq[k] = RR_LDG(&m.pair_gquat[4 * p + k]); }
+    for (int k = 0; k < 4; k++) { xq[k] = c.xquat[4 * b + k]; gq[k] = RF(pair_gquat, 4 * p + k); }
     rotq(r, gl, xq);
 #pragma unroll
     for (int k = 0; k < 3; k++) gp[k] = c.xpos[3 * b + k] + r[k];
@@ -759,39 +845,46 @@ RR_DEV void collision(Ctx<NS> &c) {
 }
 
 /* ------------------------------------------------------------------------------------------ constraint rows (B.5) */
-/* rows: jv[r] = J_r . v for the compact active rows; v staged in vbuf by the caller (already synced). */
+/* Active contact k (compact index) carries: cact[k] = contact id, cmeta[4k..4k+3] = {Jadr, chain length, rowadr of the
+ * chain's last dof, last dof}.  Its Jacobian block is 3 x len floats at Jbase(k): shared memory while the running
+ * offset fits capJ, else the per-warp global scratch (rare: e.g. every paw and tail capsule touching at once). */
+template <int NS>
+RR_DEV const float *jblock(const Ctx<NS> &c, int k) {
+  int jadr = c.cmeta[4 * k], len = c.cmeta[4 * k + 1];
+  return (jadr + 3 * len <= c.m.sm.capJ) ? c.con_J + jadr : c.gJ + jadr;
+}
+
+/* rows: out[r] = J_r . v for the compact active rows; v staged in vbuf by the caller (already synced). */
 template <int NS>
 RR_DEV void mul_j(Ctx<NS> &c, float *out) {
   const RRModelDev &m = c.m;
   for (int r = c.lane; r < c.nla; r += 32) {
     int id = c.row_id[r];
     float sg = (id & RR_SIGN_BIT) ? -1.f : 1.f;
-    out[r] = sg * c.vbuf[RR_LDG(&m.limit_dofadr[id & 0xffff])];
+    out[r] = sg * c.vbuf[RI(limit_dofadr, id & 0xffff)];
   }
-  /* contacts: 3 frame-row dot products per contact into con_dist[3k..] scratch (dist no longer needed) */
-  float *a3 = c.con_pos; /* 3 * ncon scratch: con_pos is dead once the Jacobians exist */
+  /* contacts: the 3 frame-row dot products per contact go to a3 (con_pos is dead once the Jacobians exist) */
+  float *a3 = c.con_pos;
   for (int it = c.lane; it < 3 * c.nca; it += 32) {
     int k = it / 3, r3 = it - 3 * k;
-    int cc = c.cact[k];
-    int p = RR_LDG(&m.con_pair[cc]);
-    int ld = RR_LDG(&m.pair_lastdof[p]);
-    int len = RR_LDG(&m.dof_depth[ld]) + 1, adr = RR_LDG(&m.dof_rowadr[ld]);
-    const float *J = c.con_J + RR_LDG(&m.con_Jadr[cc]) + r3 * len;
+    int len = c.cmeta[4 * k + 1], adr = c.cmeta[4 * k + 2];
+    const float *J = jblock<NS>(c, k) + r3 * len;
     float acc = 0.f;
-    for (int t = 0; t < len; t++) acc += J[t] * c.vbuf[RR_LDG(&m.M_colind[adr + t])];
+#pragma unroll 2
+    for (int t = 0; t < len; t++) acc += J[t] * c.vbuf[RR_META_COL(RI(M_meta, adr + t))];
     a3[it] = acc;
   }
   __syncwarp();
   for (int r = c.lane; r < 4 * c.nca; r += 32) {
     int k = r >> 2, q = r & 3;
-    float mu = RR_LDG(&m.pair_mu[RR_LDG(&m.con_pair[c.cact[k]])]);
+    float mu = RF(pair_mu, RI(con_pair, c.cact[k]));
     float f = (q & 1) ? -mu : mu;
     out[c.nla + r] = a3[3 * k] + a3[3 * k + 1 + (q >> 1)] * f;
   }
   __syncwarp();
 }
 
-/* qfc = J' f for the compact active rows; f in `frc` (smem rows) */
+/* qfc = J' f for the compact active rows; f in `frc` (rows) */
 template <int NS>
 RR_DEV void mul_jt(Ctx<NS> &c, const float *frc, float (&qfc)[NS]) {
   const RRModelDev &m = c.m;
@@ -802,11 +895,11 @@ RR_DEV void mul_jt(Ctx<NS> &c, const float *frc, float (&qfc)[NS]) {
   for (int r = c.lane; r < c.nla; r += 32) {
     int id = c.row_id[r];
     float sg = (id & RR_SIGN_BIT) ? -1.f : 1.f;
-    c.vbuf[RR_LDG(&m.limit_dofadr[id & 0xffff])] = sg * frc[r];
+    c.vbuf[RI(limit_dofadr, id & 0xffff)] = sg * frc[r];
   }
   for (int k = c.lane; k < c.nca; k += 32) {
     const float *f = frc + c.nla + 4 * k;
-    float mu = RR_LDG(&m.pair_mu[RR_LDG(&m.con_pair[c.cact[k]])]);
+    float mu = RF(pair_mu, RI(con_pair, c.cact[k]));
     g3[3 * k] = f[0] + f[1] + f[2] + f[3];
     g3[3 * k + 1] = mu * f[0] - mu * f[1];
     g3[3 * k + 2] = mu * f[2] - mu * f[3];
@@ -818,11 +911,10 @@ RR_DEV void mul_jt(Ctx<NS> &c, const float *frc, float (&qfc)[NS]) {
     if (i < m.nv) {
       acc = c.vbuf[i];
       for (int k = 0; k < c.nca; k++) {
-        int cc = c.cact[k];
-        int ld = RR_LDG(&m.pair_lastdof[RR_LDG(&m.con_pair[cc])]);
+        int ld = c.cmeta[4 * k + 3];
         if (i <= ld && ld <= i + c.nd[s]) {
-          int len = RR_LDG(&m.dof_depth[ld]) + 1;
-          const float *J = c.con_J + RR_LDG(&m.con_Jadr[cc]) + c.dep[s];
+          int len = c.cmeta[4 * k + 1];
+          const float *J = jblock<NS>(c, k) + c.dep[s];
           acc += J[0] * g3[3 * k] + J[len] * g3[3 * k + 1] + J[2 * len] * g3[3 * k + 2];
         }
       }
@@ -836,62 +928,85 @@ template <int NS>
 RR_DEV void make_constraint(Ctx<NS> &c) {
   const RRModelDev &m = c.m;
   const unsigned lt = (1u << c.lane) - 1u;
-  /* joint limits */
-  int nla = 0;
+  /* pass 1: count the active limit rows and contacts, then pick the row storage (shared memory up to capR rows) */
+  int nla = 0, nca = 0;
+  for (int base = 0; base < m.nlimit; base += 32) {
+    int l = base + c.lane;
+    bool active = false;
+    if (l < m.nlimit) {
+      float q = c.qpos[RI(limit_qposadr, l)];
+      float pos = fminf(q - RF(limit_range, 2 * l), RF(limit_range, 2 * l + 1) - q) - RF(limit_margin, l);
+      active = pos < 0.f;
+    }
+    nla += __popc(__ballot_sync(RR_FULL, active));
+  }
+  for (int base = 0; base < m.ncon; base += 32) {
+    int cc = base + c.lane;
+    bool active = false;
+    if (cc < m.ncon) active = (c.con_dist[cc] - RF(pair_margin, RI(con_pair, cc))) < 0.f;
+    unsigned mask = __ballot_sync(RR_FULL, active);
+    if (active) c.cact[nca + __popc(mask & lt)] = cc;
+    nca += __popc(mask);
+  }
+  const int nra = nla + 4 * nca;
+  c.nla = nla;
+  c.nca = nca;
+  c.use_rows(nra <= m.sm.capR);
+  __syncwarp();
+  /* pass 2: limit rows */
+  int r0 = 0;
   for (int base = 0; base < m.nlimit; base += 32) {
     int l = base + c.lane;
     bool active = false;
     float pos = 0.f, dlo = 0.f, dhi = 0.f;
     if (l < m.nlimit) {
-      float q = c.qpos[RR_LDG(&m.limit_qposadr[l])];
-      dlo = q - RR_LDG(&m.limit_range[2 * l]);
-      dhi = RR_LDG(&m.limit_range[2 * l + 1]) - q;
-      pos = fminf(dlo, dhi) - RR_LDG(&m.limit_margin[l]);
+      float q = c.qpos[RI(limit_qposadr, l)];
+      dlo = q - RF(limit_range, 2 * l);
+      dhi = RF(limit_range, 2 * l + 1) - q;
+      pos = fminf(dlo, dhi) - RF(limit_margin, l);
       active = pos < 0.f;
     }
     unsigned mask = __ballot_sync(RR_FULL, active);
     if (active) {
-      int r = nla + __popc(mask & lt);
-      float sr[2] = {RR_LDG(&m.limit_solref[2 * l]), RR_LDG(&m.limit_solref[2 * l + 1])}, si[5], k, b, imp;
+      int r = r0 + __popc(mask & lt);
+      float sr[2] = {RF(limit_solref, 2 * l), RF(limit_solref, 2 * l + 1)}, si[5], k, b, imp;
 #pragma unroll
-      for (int q = 0; q < 5; q++) si[q] = RR_LDG(&m.limit_solimp[5 * l + q]);
+      for (int q = 0; q < 5; q++) si[q] = RF(limit_solimp, 5 * l + q);
       kbi(m.timestep, sr, si, pos, k, b, imp);
-      float R = fmaxf(RR_LDG(&m.limit_invweight[l]) * (1.f - imp) / imp, RR_MINVAL);
+      float R = fmaxf(RF(limit_invweight, l) * (1.f - imp) / imp, RR_MINVAL);
       c.row_id[r] = l | (dlo < dhi ? 0 : RR_SIGN_BIT);
       c.row_D[r] = 1.f / R;
       c.row_aref[r] = k * imp * pos; /* temp: completed below */
       c.row_Jaref[r] = b;            /* temp */
     }
-    nla += __popc(mask);
+    r0 += __popc(mask);
   }
-  /* contacts */
-  int nca = 0;
-  for (int base = 0; base < m.ncon; base += 32) {
-    int cc = base + c.lane;
-    bool active = false;
-    if (cc < m.ncon) active = (c.con_dist[cc] - RR_LDG(&m.pair_margin[RR_LDG(&m.con_pair[cc])])) < 0.f;
-    unsigned mask = __ballot_sync(RR_FULL, active);
-    if (active) c.cact[nca + __popc(mask & lt)] = cc;
-    nca += __popc(mask);
+  /* contact metadata: running Jacobian offsets (serial prefix over <= ncon active contacts, done by every lane) */
+  {
+    int jadr = 0;
+    for (int k = 0; k < nca; k++) {
+      int p = RI(con_pair, c.cact[k]);
+      int ld = RI(pair_lastdof, p);
+      int len = RI(dof_depth, ld) + 1;
+      if (c.lane == 0) { c.cmeta[4 * k] = jadr; c.cmeta[4 * k + 1] = len; c.cmeta[4 * k + 2] = RI(dof_rowadr, ld); c.cmeta[4 * k + 3] = ld; }
+      jadr += 3 * len;
+    }
   }
-  c.nla = nla;
-  c.nca = nca;
   __syncwarp();
   /* contact Jacobian blocks (3 x chain) and row parameters */
   for (int k = 0; k < nca; k++) {
     int cc = c.cact[k];
-    int p = RR_LDG(&m.con_pair[cc]);
-    int ld = RR_LDG(&m.pair_lastdof[p]);
-    int len = RR_LDG(&m.dof_depth[ld]) + 1, adr = RR_LDG(&m.dof_rowadr[ld]);
-    int rs = RR_LDG(&m.body_rootslot[RR_LDG(&m.pair_body[p])]);
+    int p = RI(con_pair, cc);
+    int len = c.cmeta[4 * k + 1], adr = c.cmeta[4 * k + 2];
+    int rs = RI(body_rootslot, RI(pair_body, p));
     float off[3], fr[9];
 #pragma unroll
     for (int q = 0; q < 3; q++) off[q] = c.con_pos[3 * cc + q] - c.com[3 * rs + q];
 #pragma unroll
     for (int q = 0; q < 9; q++) fr[q] = c.con_frame[9 * cc + q];
-    float *J = c.con_J + RR_LDG(&m.con_Jadr[cc]);
+    float *J = const_cast<float *>(jblock<NS>(c, k));
     for (int t = c.lane; t < len; t += 32) {
-      int d = RR_LDG(&m.M_colind[adr + t]);
+      int d = RR_META_COL(RI(M_meta, adr + t));
       float cd[6], cr[3], jp[3];
 #pragma unroll
       for (int q = 0; q < 6; q++) cd[q] = c.cdof[6 * d + q];
@@ -902,12 +1017,12 @@ RR_DEV void make_constraint(Ctx<NS> &c) {
       for (int r3 = 0; r3 < 3; r3++) J[r3 * len + t] = fr[3 * r3] * jp[0] + fr[3 * r3 + 1] * jp[1] + fr[3 * r3 + 2] * jp[2];
     }
     if (c.lane < 4) {
-      float pos = c.con_dist[cc] - RR_LDG(&m.pair_margin[p]);
-      float sr[2] = {RR_LDG(&m.pair_solref[2 * p]), RR_LDG(&m.pair_solref[2 * p + 1])}, si[5], kk, b, imp;
+      float pos = c.con_dist[cc] - RF(pair_margin, p);
+      float sr[2] = {RF(pair_solref, 2 * p), RF(pair_solref, 2 * p + 1)}, si[5], kk, b, imp;
 #pragma unroll
-      for (int q = 0; q < 5; q++) si[q] = RR_LDG(&m.pair_solimp[5 * p + q]);
+      for (int q = 0; q < 5; q++) si[q] = RF(pair_solimp, 5 * p + q);
       kbi(m.timestep, sr, si, pos, kk, b, imp);
-      float mu = RR_LDG(&m.pair_mu[p]), t = RR_LDG(&m.pair_invweight[p]);
+      float mu = RF(pair_mu, p), t = RF(pair_invweight, p);
       float invw = (t + mu * mu * t) * 2.f * mu * mu / m.impratio;
       float R = fmaxf(invw * (1.f - imp) / imp, RR_MINVAL);
       int r = nla + 4 * k + c.lane;
@@ -919,25 +1034,23 @@ RR_DEV void make_constraint(Ctx<NS> &c) {
   }
   __syncwarp();
   /* debug: dense efc_J / efc_D in MJX row order (inactive rows are zero there) */
-  if (c.dbg) {
+  if (RR_WITH_DEBUG && c.dbg) {
     float *dJ = c.dbg + dbg_offset(m, RR_DBG_EFC_J), *dD = c.dbg + dbg_offset(m, RR_DBG_EFC_D);
     for (int i = c.lane; i < m.nefc * m.nv; i += 32) dJ[i] = 0.f;
     for (int i = c.lane; i < m.nefc; i += 32) dD[i] = 1.f / RR_MINVAL;
     __syncwarp();
     for (int r = c.lane; r < nla; r += 32) {
       int id = c.row_id[r], l = id & 0xffff;
-      dJ[l * m.nv + RR_LDG(&m.limit_dofadr[l])] = (id & RR_SIGN_BIT) ? -1.f : 1.f;
+      dJ[l * m.nv + RI(limit_dofadr, l)] = (id & RR_SIGN_BIT) ? -1.f : 1.f;
       dD[l] = c.row_D[r];
     }
     for (int k = 0; k < nca; k++) {
       int cc = c.cact[k];
-      int p = RR_LDG(&m.con_pair[cc]);
-      int ld = RR_LDG(&m.pair_lastdof[p]);
-      int len = RR_LDG(&m.dof_depth[ld]) + 1, adr = RR_LDG(&m.dof_rowadr[ld]);
-      const float *J = c.con_J + RR_LDG(&m.con_Jadr[cc]);
-      float mu = RR_LDG(&m.pair_mu[p]);
+      int len = c.cmeta[4 * k + 1], adr = c.cmeta[4 * k + 2];
+      const float *J = jblock<NS>(c, k);
+      float mu = RF(pair_mu, RI(con_pair, cc));
       for (int t = c.lane; t < len; t += 32) {
-        int d = RR_LDG(&m.M_colind[adr + t]);
+        int d = RR_META_COL(RI(M_meta, adr + t));
         for (int q = 0; q < 4; q++) {
           float f = (q & 1) ? -mu : mu;
           dJ[(m.nlimit + 4 * cc + q) * m.nv + d] = J[t] + J[(1 + (q >> 1)) * len + t] * f;
@@ -948,13 +1061,12 @@ RR_DEV void make_constraint(Ctx<NS> &c) {
     __syncwarp();
   }
   /* aref = -b (J qvel) - k imp pos */
-  int nra = nla + 4 * nca;
   for (int i = c.lane; i < m.nv; i += 32) c.vbuf[i] = c.qvel[i];
   __syncwarp();
   mul_j<NS>(c, c.row_jv);
   for (int r = c.lane; r < nra; r += 32) c.row_aref[r] = -c.row_Jaref[r] * c.row_jv[r] - c.row_aref[r];
   __syncwarp();
-  if (c.dbg) {
+  if (RR_WITH_DEBUG && c.dbg) {
     float *dA = c.dbg + dbg_offset(m, RR_DBG_EFC_AREF);
     for (int i = c.lane; i < m.nefc; i += 32) dA[i] = 0.f;
     __syncwarp();
@@ -966,56 +1078,73 @@ RR_DEV void make_constraint(Ctx<NS> &c) {
 /* ------------------------------------------------------------------------------------------ solver (B.7) */
 struct LSPoint { float alpha, cost, d0, d1; };
 
-template <int NS>
-RR_DEV LSPoint ls_eval(Ctx<NS> &c, int nra, float alpha, float g0, float g1, float g2) {
-  float q0 = 0.f, q1 = 0.f, q2 = 0.f;
+/* _LSPoint.create at NA step sizes in one pass over the active rows (the three candidates of a line-search
+ * iteration share the row loads; their 3 NA partial sums are reduced with interleaved shuffles). */
+template <int NS, int NA>
+RR_DEV void ls_eval(Ctx<NS> &c, int nra, const float (&alpha)[NA], float g0, float g1, float g2, LSPoint (&out)[NA]) {
+  float q[NA][3];
+#pragma unroll
+  for (int k = 0; k < NA; k++) q[k][0] = q[k][1] = q[k][2] = 0.f;
   for (int r = c.lane; r < nra; r += 32) {
     float ja = c.row_Jaref[r], jv = c.row_jv[r], D = c.row_D[r];
-    if (ja + alpha * jv < 0.f) {
-      q0 += 0.5f * ja * ja * D; q1 += jv * ja * D; q2 += 0.5f * jv * jv * D;
+    float a0 = 0.5f * ja * ja * D, a1 = jv * ja * D, a2 = 0.5f * jv * jv * D;
+#pragma unroll
+    for (int k = 0; k < NA; k++) {
+      if (ja + alpha[k] * jv < 0.f) { q[k][0] += a0; q[k][1] += a1; q[k][2] += a2; }
     }
   }
-  q0 = g0 + warp_sum(q0); q1 = g1 + warp_sum(q1); q2 = g2 + warp_sum(q2);
-  LSPoint p;
-  p.alpha = alpha;
-  p.cost = alpha * alpha * q2 + alpha * q1 + q0;
-  p.d0 = 2.f * alpha * q2 + q1;
-  p.d1 = 2.f * q2 + (q2 == 0.f ? RR_MINVAL : 0.f);
-  return p;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int k = 0; k < NA; k++) {
+#pragma unroll
+      for (int d = 0; d < 3; d++) q[k][d] += __shfl_xor_sync(RR_FULL, q[k][d], o);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NA; k++) {
+    float q0 = g0 + q[k][0], q1 = g1 + q[k][1], q2 = g2 + q[k][2], al = alpha[k];
+    out[k].alpha = al;
+    out[k].cost = al * al * q2 + al * q1 + q0;
+    out[k].d0 = 2.f * al * q2 + q1;
+    out[k].d1 = 2.f * q2 + (q2 == 0.f ? RR_MINVAL : 0.f);
+  }
 }
 
 /* Given qacc (regs): Ma = M qacc, Jaref = J qacc - aref (rows, smem). */
 template <int NS>
 RR_DEV void ctx_init(Ctx<NS> &c, const float (&qacc)[NS], float (&Ma)[NS]) {
   mul_m<NS>(c, Ma, qacc); /* leaves qacc staged in vbuf */
-  vstore<NS>(c, qacc, c.vbuf);
-  __syncwarp();
   mul_j<NS>(c, c.row_Jaref);
   int nra = c.nla + 4 * c.nca;
   for (int r = c.lane; r < nra; r += 32) c.row_Jaref[r] -= c.row_aref[r];
   __syncwarp();
 }
 
-/* _update_constraint: forces (into row_jv), qfrc_constraint, returns total cost; gauss out */
+/* constraint + Gauss cost at (qacc, Ma, Jaref); with_force also stores efc_force in row_jv */
 template <int NS>
-RR_DEV float update_constraint(Ctx<NS> &c, const float (&qacc)[NS], const float (&Ma)[NS], float (&qfc)[NS], float &gauss,
-                               bool need_force) {
+RR_DEV float constraint_cost(Ctx<NS> &c, const float (&qacc)[NS], const float (&Ma)[NS], float &gauss, bool with_force) {
   int nra = c.nla + 4 * c.nca;
   float cost = 0.f;
   for (int r = c.lane; r < nra; r += 32) {
     float ja = c.row_Jaref[r], D = c.row_D[r];
     bool act = ja < 0.f;
-    c.row_jv[r] = act ? D * -ja : 0.f;
+    if (with_force) c.row_jv[r] = act ? D * -ja : 0.f;
     if (act) cost += D * ja * ja;
   }
-  cost = 0.5f * warp_sum(cost);
   float g = 0.f;
   RR_FOR_S g += (Ma[s] - c.qfrc_smooth[s]) * (qacc[s] - c.qacc_smooth[s]);
-  gauss = 0.5f * warp_sum(g);
-  if (need_force) mul_jt<NS>(c, c.row_jv, qfc);
-  return cost + gauss;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    cost += __shfl_xor_sync(RR_FULL, cost, o);
+    g += __shfl_xor_sync(RR_FULL, g, o);
+  }
+  gauss = 0.5f * g;
+  return 0.5f * cost + gauss;
 }
 
+/* solver.solve (CG).  The loop is arranged so that each heavy routine (mul_m, mul_j, mul_jt, solve_ld) has one call
+ * site: the kernel is instruction-cache bound otherwise (ncu: stall_no_instruction). */
 template <int NS>
 RR_DEV void solve_constraints(Ctx<NS> &c) {
   const RRModelDev &m = c.m;
@@ -1023,98 +1152,121 @@ RR_DEV void solve_constraints(Ctx<NS> &c) {
   const float nvf = (float)(m.nv > 1 ? m.nv : 1);
   const float scale = 1.f / (m.meaninertia * nvf);
   float Ma[NS], grad[NS], Mgrad[NS], search[NS], mv[NS];
-  float gauss, cost, prev_cost;
-  /* warm start: keep whichever of qacc_warmstart / qacc_smooth has the lower cost */
+  float gauss = 0.f, cost = INFINITY, prev_cost = INFINITY, beta = 0.f;
+  RR_FOR_S mv[s] = 0.f;
+  /* warm start: keep whichever of qacc_smooth / qacc_warmstart has the lower cost (candidate 2 = back to smooth) */
   {
-    float cs, cw, g;
-    ctx_init<NS>(c, c.qacc_smooth, Ma);
-    cs = update_constraint<NS>(c, c.qacc_smooth, Ma, c.qfrc_constraint, g, false);
-    ctx_init<NS>(c, c.warm, Ma);
-    cw = update_constraint<NS>(c, c.warm, Ma, c.qfrc_constraint, g, false);
-    if (cw < cs) {
-      RR_FOR_S c.qacc[s] = c.warm[s];
-    } else {
-      RR_FOR_S c.qacc[s] = c.qacc_smooth[s];
+    float cs = 0.f, cw = 0.f, g;
+    for (int cand = 0; cand < 3; cand++) {
+      if (cand == 2 && cw < cs) break;
+      RR_FOR_S c.qacc[s] = (cand == 1) ? c.warm[s] : c.qacc_smooth[s];
       ctx_init<NS>(c, c.qacc, Ma);
+      if (cand == 2) break;
+      float cst = constraint_cost<NS>(c, c.qacc, Ma, g, false);
+      if (cand == 0) cs = cst; else cw = cst;
     }
   }
-  cost = update_constraint<NS>(c, c.qacc, Ma, c.qfrc_constraint, gauss, true);
-  prev_cost = INFINITY;
-  RR_FOR_S { grad[s] = Ma[s] - c.qfrc_smooth[s] - c.qfrc_constraint[s]; Mgrad[s] = grad[s]; }
-  solve_ld<NS>(c, Mgrad);
-  RR_FOR_S search[s] = -Mgrad[s];
   prof<NS>(c, RR_PROF_SOLVE_INIT);
   int niter = 0;
+  bool first = true;
   for (;;) {
-    if (m.iterations != 1) {
-      float improvement = (prev_cost - cost) * scale;
-      float gradient = sqrtf(vdot<NS>(grad, grad)) * scale;
-      if (niter >= m.iterations || improvement < m.tolerance || gradient < m.tolerance) break;
-    } else if (niter >= 1) {
-      break;
-    }
-    /* ---- linesearch ---- */
-    float smag = sqrtf(vdot<NS>(search, search)) * m.meaninertia * nvf;
-    float gtol = m.tolerance * m.ls_tolerance * smag;
-    mul_m<NS>(c, mv, search); /* search stays staged in vbuf */
-    vstore<NS>(c, search, c.vbuf);
-    __syncwarp();
-    mul_j<NS>(c, c.row_jv);
-    float g0 = gauss;
-    float g1 = vdot<NS>(search, Ma) - vdot<NS>(search, c.qfrc_smooth);
-    float g2 = 0.5f * vdot<NS>(search, mv);
-    LSPoint p0 = ls_eval<NS>(c, nra, 0.f, g0, g1, g2);
-    LSPoint lo = ls_eval<NS>(c, nra, p0.alpha - p0.d0 / p0.d1, g0, g1, g2), hi;
-    if (lo.d0 < p0.d0) { hi = p0; } else { hi = lo; lo = p0; }
-    bool swap = true;
-    int ls_iter = 0;
-    for (;;) {
-      bool done = ls_iter >= m.ls_iterations;
-      done |= !swap;
-      done |= (lo.d0 < 0.f) && (lo.d0 > -gtol);
-      done |= (hi.d0 > 0.f) && (hi.d0 < gtol);
-      if (done) break;
-      LSPoint lo_next = ls_eval<NS>(c, nra, lo.alpha - lo.d0 / lo.d1, g0, g1, g2);
-      LSPoint hi_next = ls_eval<NS>(c, nra, hi.alpha - hi.d0 / hi.d1, g0, g1, g2);
-      LSPoint mid = ls_eval<NS>(c, nra, 0.5f * (lo.alpha + hi.alpha), g0, g1, g2);
-      bool swap_lo_next = (lo.d0 > 0.f) || (lo.d0 < lo_next.d0);
-      if (swap_lo_next) lo = lo_next;
-      bool swap_lo_mid = (mid.d0 < 0.f) && (lo.d0 < mid.d0);
-      if (swap_lo_mid) lo = mid;
-      bool swap_hi_next = (hi.d0 < 0.f) || (hi.d0 > hi_next.d0);
-      if (swap_hi_next) hi = hi_next;
-      bool swap_hi_mid = (mid.d0 > 0.f) && (hi.d0 > mid.d0);
-      if (swap_hi_mid) hi = mid;
-      swap = swap_lo_next | swap_lo_mid | swap_hi_next | swap_hi_mid;
-      ls_iter++;
-    }
-    bool improved = (lo.cost < p0.cost) || (hi.cost < p0.cost);
-    float alpha = lo.cost < hi.cost ? lo.alpha : hi.alpha;
-    if (improved) {
-      RR_FOR_S { c.qacc[s] += search[s] * alpha; Ma[s] += mv[s] * alpha; }
-      for (int r = c.lane; r < nra; r += 32) c.row_Jaref[r] += c.row_jv[r] * alpha;
-      __syncwarp();
-    }
-    prof<NS>(c, RR_PROF_SOLVE_LS);
-    /* ---- update ---- */
     float prev_grad[NS], prev_Mgrad[NS];
-    RR_FOR_S { prev_grad[s] = grad[s]; prev_Mgrad[s] = Mgrad[s]; }
+    if (!first) {
+      if (m.iterations != 1) {
+        float improvement = (prev_cost - cost) * scale;
+        float gradient = sqrtf(vdot<NS>(grad, grad)) * scale;
+        if (niter >= m.iterations || improvement < m.tolerance || gradient < m.tolerance) break;
+      } else if (niter >= 1) {
+        break;
+      }
+      /* ---- linesearch ---- */
+      float smag = sqrtf(vdot<NS>(search, search)) * m.meaninertia * nvf;
+      float gtol = m.tolerance * m.ls_tolerance * smag;
+      /* mv = M search.  search = -Mgrad + beta search_prev with M Mgrad = grad (Mgrad is the LD solve of grad), so
+       * mv = -grad + beta mv_prev: the same vector MJX gets from mul_m(search), without the product. */
+      RR_FOR_S mv[s] = -grad[s] + beta * mv[s];
+      __syncwarp();
+      vstore<NS>(c, search, c.vbuf);
+      __syncwarp();
+      mul_j<NS>(c, c.row_jv);
+      float g0 = gauss, g1 = 0.f, g2 = 0.f;
+      RR_FOR_S { g1 += search[s] * (Ma[s] - c.qfrc_smooth[s]); g2 += search[s] * mv[s]; }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        g1 += __shfl_xor_sync(RR_FULL, g1, o);
+        g2 += __shfl_xor_sync(RR_FULL, g2, o);
+      }
+      g2 *= 0.5f;
+      LSPoint p0, lo, hi;
+      {
+        float a1[1] = {0.f};
+        LSPoint r1[1];
+        for (int pass = 0; pass < 2; pass++) {
+          ls_eval<NS, 1>(c, nra, a1, g0, g1, g2, r1);
+          if (pass == 0) { p0 = r1[0]; a1[0] = p0.alpha - p0.d0 / p0.d1; }
+        }
+        lo = r1[0];
+      }
+      if (lo.d0 < p0.d0) { hi = p0; } else { hi = lo; lo = p0; }
+      bool swap = true;
+      int ls_iter = 0;
+      for (;;) {
+        bool done = ls_iter >= m.ls_iterations;
+        done |= !swap;
+        done |= (lo.d0 < 0.f) && (lo.d0 > -gtol);
+        done |= (hi.d0 > 0.f) && (hi.d0 < gtol);
+        if (done) break;
+        float a3[3] = {lo.alpha - lo.d0 / lo.d1, hi.alpha - hi.d0 / hi.d1, 0.5f * (lo.alpha + hi.alpha)};
+        LSPoint r3[3];
+        ls_eval<NS, 3>(c, nra, a3, g0, g1, g2, r3);
+        LSPoint lo_next = r3[0], hi_next = r3[1], mid = r3[2];
+        bool swap_lo_next = (lo.d0 > 0.f) || (lo.d0 < lo_next.d0);
+        if (swap_lo_next) lo = lo_next;
+        bool swap_lo_mid = (mid.d0 < 0.f) && (lo.d0 < mid.d0);
+        if (swap_lo_mid) lo = mid;
+        bool swap_hi_next = (hi.d0 < 0.f) || (hi.d0 > hi_next.d0);
+        if (swap_hi_next) hi = hi_next;
+        bool swap_hi_mid = (mid.d0 > 0.f) && (hi.d0 > mid.d0);
+        if (swap_hi_mid) hi = mid;
+        swap = swap_lo_next | swap_lo_mid | swap_hi_next | swap_hi_mid;
+        ls_iter++;
+      }
+      bool improved = (lo.cost < p0.cost) || (hi.cost < p0.cost);
+      float alpha = lo.cost < hi.cost ? lo.alpha : hi.alpha;
+      if (improved) {
+        RR_FOR_S { c.qacc[s] += search[s] * alpha; Ma[s] += mv[s] * alpha; }
+        for (int r = c.lane; r < nra; r += 32) c.row_Jaref[r] += c.row_jv[r] * alpha;
+        __syncwarp();
+      }
+      RR_FOR_S { prev_grad[s] = grad[s]; prev_Mgrad[s] = Mgrad[s]; }
+      prof<NS>(c, RR_PROF_SOLVE_LS);
+    }
+    /* ---- _update_constraint + _update_gradient ---- */
     prev_cost = cost;
-    cost = update_constraint<NS>(c, c.qacc, Ma, c.qfrc_constraint, gauss, true);
+    cost = constraint_cost<NS>(c, c.qacc, Ma, gauss, true);
+    mul_jt<NS>(c, c.row_jv, c.qfrc_constraint);
     RR_FOR_S { grad[s] = Ma[s] - c.qfrc_smooth[s] - c.qfrc_constraint[s]; Mgrad[s] = grad[s]; }
     solve_ld<NS>(c, Mgrad);
-    float num = 0.f;
-    RR_FOR_S num += grad[s] * (Mgrad[s] - prev_Mgrad[s]);
-    num = warp_sum(num);
-    float den = fmaxf(RR_MINVAL, vdot<NS>(prev_grad, prev_Mgrad));
-    float beta = fmaxf(0.f, num / den);
-    RR_FOR_S search[s] = -Mgrad[s] + beta * search[s];
-    niter++;
+    if (first) {
+      RR_FOR_S search[s] = -Mgrad[s];
+      first = false;
+    } else {
+      float num = 0.f, den = 0.f;
+      RR_FOR_S { num += grad[s] * (Mgrad[s] - prev_Mgrad[s]); den += prev_grad[s] * prev_Mgrad[s]; }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        num += __shfl_xor_sync(RR_FULL, num, o);
+        den += __shfl_xor_sync(RR_FULL, den, o);
+      }
+      beta = fmaxf(0.f, num / fmaxf(RR_MINVAL, den));
+      RR_FOR_S search[s] = -Mgrad[s] + beta * search[s];
+      niter++;
+    }
     prof<NS>(c, RR_PROF_SOLVE_UPD);
   }
   c.niter = niter;
   RR_FOR_S c.warm[s] = c.qacc[s];
-  if (c.dbg) {
+  if (RR_WITH_DEBUG && c.dbg) {
     float *dF = c.dbg + dbg_offset(m, RR_DBG_EFC_FORCE), *dS = c.dbg + dbg_offset(m, RR_DBG_SCALARS);
     for (int i = c.lane; i < m.nefc; i += 32) dF[i] = 0.f;
     __syncwarp();
@@ -1126,10 +1278,46 @@ RR_DEV void solve_constraints(Ctx<NS> &c) {
   }
 }
 
-/* ------------------------------------------------------------------------------------------ forward / euler */
+/* The observation slices cinert[1:], cvel[1:], qfrc_actuator (Rodent_Env_Brax.py:152-156) and the optional raw views are
+ * stored to HBM right after the smooth-force stage of the last forward pass: their shared memory is recycled by the
+ * constraint phase.  (brax reports them from the forward pass at the pre-integration qpos, which is this one.) */
 template <int NS>
-RR_DEV void forward(Ctx<NS> &c) {
+RR_DEV void forward_outputs(Ctx<NS> &c) {
   const RRModelDev &m = c.m;
+  const RRStepArgs &a = c.a;
+  const size_t e = (size_t)c.env;
+  const int lane = c.lane, nb1 = m.nbody - 1;
+  if (lane < 4 && m.nbody > 1) c.xq1[lane] = c.xquat[4 + lane];
+  __syncwarp();
+  if (!c.live) return;
+  if (a.obs) {
+    const int obs_dim = m.nq + m.nv + 16 * nb1 + m.nv + 3;
+    float *o = a.obs + e * obs_dim + m.nq + m.nv;
+#pragma unroll 1
+    for (int i = lane; i < 10 * nb1; i += 32) o[i] = c.cinert[10 + i];
+    o += 10 * nb1;
+#pragma unroll 1
+    for (int i = lane; i < 6 * nb1; i += 32) o[i] = c.cvel[6 + i];
+    o += 6 * nb1;
+#pragma unroll 1
+    for (int i = lane; i < m.nv; i += 32) o[i] = c.qfrc_act[i];
+  }
+  if (a.xpos) for (int i = lane; i < 3 * m.nbody; i += 32) a.xpos[e * 3 * m.nbody + i] = c.xpos[i];
+  if (a.xquat) for (int i = lane; i < 4 * m.nbody; i += 32) a.xquat[e * 4 * m.nbody + i] = c.xquat[i];
+  if (a.subtree_com) for (int i = lane; i < 3 * m.nroot; i += 32) a.subtree_com[e * 3 * m.nroot + i] = c.com[i];
+  if (a.qfrc_actuator) for (int i = lane; i < m.nv; i += 32) a.qfrc_actuator[e * m.nv + i] = c.qfrc_act[i];
+  if (a.cinert) for (int i = lane; i < 10 * m.nbody; i += 32) a.cinert[e * 10 * m.nbody + i] = c.cinert[i];
+  if (a.cvel) for (int i = lane; i < 6 * m.nbody; i += 32) a.cvel[e * 6 * m.nbody + i] = c.cvel[i];
+}
+
+/* ------------------------------------------------------------------------------------------ forward / euler */
+/* One mjx.step: forward (B.1-B.7) then, if `integrate`, the implicit-damping Euler update (B.8).  The two
+ * factorisations (M for the solver, M + dt diag(damping) for Euler) and their solves share one call site. */
+template <int NS>
+RR_DEV void substep(Ctx<NS> &c, bool integrate, float &time) {
+  const RRModelDev &m = c.m;
+  const float dt = m.timestep;
+  RR_CTA_SYNC();
   kinematics<NS>(c);
   prof<NS>(c, RR_PROF_FK);
   com_pos<NS>(c);
@@ -1141,76 +1329,89 @@ RR_DEV void forward(Ctx<NS> &c) {
   dbg_copy<NS>(c, RR_DBG_CDOF, c.cdof, 6 * m.nv);
   crb_and_mass_matrix<NS>(c);
   prof<NS>(c, RR_PROF_QM);
-  factor<NS>(c, 0.f);
-  prof<NS>(c, RR_PROF_FACTOR);
-  dbg_copy<NS>(c, RR_DBG_M, c.M, m.nM);
-  dbg_copy<NS>(c, RR_DBG_LD, c.LD, m.nM);
-  float qfrc_bias[NS];
-  com_vel_and_rne<NS>(c, qfrc_bias);
-  prof<NS>(c, RR_PROF_RNE);
-  dbg_copy<NS>(c, RR_DBG_CVEL, c.cvel, 6 * m.nbody);
-  smooth_forces<NS>(c, qfrc_bias);
-  prof<NS>(c, RR_PROF_SMOOTH);
-  if (m.nefc == 0) {
-    RR_FOR_S { c.qacc[s] = c.qacc_smooth[s]; c.qfrc_constraint[s] = 0.f; }
-    return;
+  {
+    float qfrc_bias[NS];
+    com_vel_and_rne<NS>(c, qfrc_bias);
+    prof<NS>(c, RR_PROF_RNE);
+    dbg_copy<NS>(c, RR_DBG_CVEL, c.cvel, 6 * m.nbody);
+    smooth_forces<NS>(c, qfrc_bias);
+    prof<NS>(c, RR_PROF_SMOOTH);
   }
-  collision<NS>(c);
-  prof<NS>(c, RR_PROF_COLLIDE);
-  make_constraint<NS>(c);
-  prof<NS>(c, RR_PROF_CONSTRAINT);
-  solve_constraints<NS>(c);
-}
-
-template <int NS>
-RR_DEV void euler(Ctx<NS> &c, float &time) {
-  const RRModelDev &m = c.m;
-  const float dt = m.timestep;
-  /* implicit joint damping: (M + dt diag(damping)) qacc = qfrc_smooth + qfrc_constraint */
-  factor<NS>(c, dt);
-  float qa[NS];
-  RR_FOR_S qa[s] = c.qfrc_smooth[s] + c.qfrc_constraint[s];
-  solve_ld<NS>(c, qa);
-  for (int u = c.lane; u < m.nu; u += 32) {
-    if (RR_LDG(&m.act_dyntype[u]) != 0) {
-      int aa = RR_LDG(&m.act_actadr[u]);
-      c.act[aa] += c.actdot[aa] * dt;
-    }
-  }
-  RR_FOR_S { int i = c.lane + 32 * s; if (i < m.nv) c.qvel[i] += qa[s] * dt; }
-  __syncwarp();
-  for (int j = c.lane; j < m.njnt; j += 32) {
-    int qadr = RR_LDG(&m.jnt_qposadr[j]), da = RR_LDG(&m.jnt_dofadr[j]);
-    if (RR_LDG(&m.jnt_type[j]) == RR_JNT_FREE) {
-#pragma unroll
-      for (int k = 0; k < 3; k++) c.qpos[qadr + k] += dt * c.qvel[da + k];
-      float v[3] = {c.qvel[da + 3], c.qvel[da + 4], c.qvel[da + 5]}, q[4], qr[4], q2[4];
-      float nrm = normalize3(v);
-      axis_angle_quat(qr, v, dt * nrm);
-#pragma unroll
-      for (int k = 0; k < 4; k++) q[k] = c.qpos[qadr + 3 + k];
-      quat_mul(q2, q, qr);
-      normalize4(q2);
-#pragma unroll
-      for (int k = 0; k < 4; k++) c.qpos[qadr + 3 + k] = q2[k];
+  if (c.last_substep) forward_outputs<NS>(c);
+  for (int pass = 0; pass < 2; pass++) {
+    RR_CTA_SYNC();
+    factor<NS>(c, pass ? dt : 0.f);
+    float x[NS];
+    RR_FOR_S x[s] = pass ? c.qfrc_smooth[s] + c.qfrc_constraint[s] : c.qfrc_smooth[s];
+    solve_ld<NS>(c, x);
+    prof<NS>(c, pass ? RR_PROF_EULER : RR_PROF_FACTOR);
+    if (pass == 0) {
+      dbg_copy<NS>(c, RR_DBG_M, c.M, m.nM);
+      dbg_copy<NS>(c, RR_DBG_LD, c.LD, m.nM);
+      RR_FOR_S c.qacc_smooth[s] = x[s];
+      dbg_vec<NS>(c, RR_DBG_QACC_SMOOTH, c.qacc_smooth);
+      if (m.nefc == 0) {
+        RR_FOR_S { c.qacc[s] = c.qacc_smooth[s]; c.qfrc_constraint[s] = 0.f; }
+      } else {
+        RR_CTA_SYNC();
+        collision<NS>(c);
+        prof<NS>(c, RR_PROF_COLLIDE);
+        make_constraint<NS>(c);
+        prof<NS>(c, RR_PROF_CONSTRAINT);
+        solve_constraints<NS>(c);
+      }
+      if (!integrate) break;
     } else {
-      c.qpos[qadr] += dt * c.qvel[da];
+      /* _advance: act, qvel, qpos (semi-implicit: positions use the new velocities) */
+      for (int u = c.lane; u < m.nu; u += 32) {
+        if (RI(act_dyntype, u) != 0) {
+          int aa = RI(act_actadr, u);
+          c.act[aa] += c.actdot[aa] * dt;
+        }
+      }
+      RR_FOR_S { int i = c.lane + 32 * s; if (i < m.nv) c.qvel[i] += x[s] * dt; }
+      __syncwarp();
+      for (int j = c.lane; j < m.njnt; j += 32) {
+        int qadr = RI(jnt_qposadr, j), da = RI(jnt_dofadr, j);
+        if (RI(jnt_type, j) == RR_JNT_FREE) {
+#pragma unroll
+          for (int k = 0; k < 3; k++) c.qpos[qadr + k] += dt * c.qvel[da + k];
+          float v[3] = {c.qvel[da + 3], c.qvel[da + 4], c.qvel[da + 5]}, q[4], qr[4], q2[4];
+          float nrm = normalize3(v);
+          axis_angle_quat(qr, v, dt * nrm);
+#pragma unroll
+          for (int k = 0; k < 4; k++) q[k] = c.qpos[qadr + 3 + k];
+          quat_mul(q2, q, qr);
+          normalize4(q2);
+#pragma unroll
+          for (int k = 0; k < 4; k++) c.qpos[qadr + 3 + k] = q2[k];
+        } else {
+          c.qpos[qadr] += dt * c.qvel[da];
+        }
+      }
+      __syncwarp();
+      time += dt;
+      prof<NS>(c, RR_PROF_EULER);
     }
   }
-  __syncwarp();
-  time += dt;
 }
 
 /* ------------------------------------------------------------------------------------------ one environment */
 template <int NS>
-RR_DEV void env_run(const RRModelDev &m, const RRStepArgs &a, int env, float *sm, int lane) {
-  Ctx<NS> c(m, a, env, sm, lane);
-  if (a.prof) c.tprev = RR_CLOCK();
+RR_DEV void env_run(const RRModelDev &m, const RRStepArgs &a, int env_in, int slot, float *sm, const int32_t *ti, const float *tf,
+                    int lane) {
+  const int env = env_in < a.B ? env_in : a.B - 1;
+  Ctx<NS> c(m, a, env, slot, sm, ti, tf, lane);
+  c.live = env_in < a.B;
+  if (!c.live) c.dbg = nullptr;
+  if (RR_WITH_DEBUG && a.prof) c.tprev = RR_CLOCK();
   const size_t e = (size_t)env;
   /* ---- load state ---- */
+#pragma unroll 1
   for (int i = lane; i < m.nq; i += 32) c.qpos[i] = a.in_qpos[e * m.nq + i];
   for (int i = lane; i < m.nv; i += 32) c.qvel[i] = a.in_qvel[e * m.nv + i];
   for (int i = lane; i < m.na; i += 32) { c.act[i] = a.in_act[e * m.na + i]; c.actdot[i] = 0.f; }
+#pragma unroll 1
   for (int i = lane; i < m.nu; i += 32) c.ctrl[i] = a.action ? a.action[e * m.nu + i] : 0.f;
   RR_FOR_S { int i = lane + 32 * s; c.warm[s] = i < m.nv ? a.in_warm[e * m.nv + i] : 0.f; }
   float time = a.in_time ? a.in_time[e] : 0.f;
@@ -1220,16 +1421,15 @@ RR_DEV void env_run(const RRModelDev &m, const RRStepArgs &a, int env, float *sm
   __syncwarp();
   prof<NS>(c, RR_PROF_LOAD);
   /* ---- physics ---- */
-  if (a.mode == RR_MODE_INIT) {
-    forward<NS>(c);
-  } else {
-    for (int sub = 0; sub < a.nsub; sub++) {
-      forward<NS>(c);
-      euler<NS>(c, time);
-      prof<NS>(c, RR_PROF_EULER);
+  {
+    const int nrun = a.mode == RR_MODE_INIT ? 1 : a.nsub;
+    for (int sub = 0; sub < nrun; sub++) {
+      c.last_substep = sub == nrun - 1;
+      substep<NS>(c, a.mode != RR_MODE_INIT, time);
     }
   }
   __syncwarp();
+  if (!c.live) return;
   /* ---- run-task epilogue (Rodent_Env_Brax.py:98-162) ---- */
   const RRTask &t = a.task;
   int cf = a.in_cur_frame ? a.in_cur_frame[e] : 0;
@@ -1260,14 +1460,18 @@ RR_DEV void env_run(const RRModelDev &m, const RRStepArgs &a, int env, float *sm
   const bool restore = a.wrap && a.mode == RR_MODE_STEP && done != 0.f; /* AutoResetWrapper */
   /* ---- state write-back ---- */
   if (restore) {
+#pragma unroll 1
     for (int i = lane; i < m.nq; i += 32) a.qpos[e * m.nq + i] = a.first_qpos[e * m.nq + i];
     for (int i = lane; i < m.nv; i += 32) a.qvel[e * m.nv + i] = a.first_qvel[e * m.nv + i];
+#pragma unroll 1
     for (int i = lane; i < m.na; i += 32) a.act[e * m.na + i] = a.first_act[e * m.na + i];
     for (int i = lane; i < m.nv; i += 32) a.warm[e * m.nv + i] = a.first_warm[e * m.nv + i];
     if (a.time && lane == 0) a.time[e] = a.first_time ? a.first_time[e] : 0.f;
   } else {
+#pragma unroll 1
     for (int i = lane; i < m.nq; i += 32) a.qpos[e * m.nq + i] = c.qpos[i];
     for (int i = lane; i < m.nv; i += 32) a.qvel[e * m.nv + i] = c.qvel[i];
+#pragma unroll 1
     for (int i = lane; i < m.na; i += 32) a.act[e * m.na + i] = c.act[i];
     RR_FOR_S { int i = lane + 32 * s; if (i < m.nv) a.warm[e * m.nv + i] = c.warm[s]; }
     if (a.time && lane == 0) a.time[e] = time;
@@ -1279,23 +1483,20 @@ RR_DEV void env_run(const RRModelDev &m, const RRStepArgs &a, int env, float *sm
     float *o = a.obs + e * obs_dim;
     if (restore) {
       const float *fo = a.first_obs + e * obs_dim;
+#pragma unroll 1
       for (int i = lane; i < obs_dim; i += 32) o[i] = fo[i];
     } else {
+#pragma unroll 1
       for (int i = lane; i < m.nq; i += 32) o[i] = c.qpos[i];
       o += m.nq;
+#pragma unroll 1
       for (int i = lane; i < m.nv; i += 32) o[i] = c.qvel[i];
-      o += m.nv;
-      for (int i = lane; i < 10 * nb1; i += 32) o[i] = c.cinert[10 + i];
-      o += 10 * nb1;
-      for (int i = lane; i < 6 * nb1; i += 32) o[i] = c.cvel[6 + i];
-      o += 6 * nb1;
-      for (int i = lane; i < m.nv; i += 32) o[i] = c.qfrc_act[i];
-      o += m.nv;
+      o += m.nv + 16 * nb1 + m.nv; /* cinert / cvel / qfrc_actuator were stored by forward_outputs */
       if (lane < 3) {
         int ti = cf_new + 1;
         ti = ti < 0 ? 0 : (ti >= t.track_len ? t.track_len - 1 : ti);
         float v[3] = {t.track_pos[3 * ti] - c.qpos[0], t.track_pos[3 * ti + 1] - c.qpos[1], t.track_pos[3 * ti + 2] - c.qpos[2]};
-        float R[9], xq[4] = {c.xquat[4], c.xquat[5], c.xquat[6], c.xquat[7]};
+        float R[9], xq[4] = {c.xq1[0], c.xq1[1], c.xq1[2], c.xq1[3]};
         quat_to_mat(R, xq);
         o[lane] = R[3 * lane] * v[0] + R[3 * lane + 1] * v[1] + R[3 * lane + 2] * v[2]; /* xmat[1] @ v (not transposed) */
       }
@@ -1309,18 +1510,11 @@ RR_DEV void env_run(const RRModelDev &m, const RRStepArgs &a, int env, float *sm
     if (a.wrap) { a.steps[e] = a.mode == RR_MODE_INIT ? 0.f : steps; a.truncation[e] = trunc; }
     if (a.niter) a.niter[e] = c.niter;
   }
-  /* optional raw outputs of the last forward pass */
-  if (a.xpos) for (int i = lane; i < 3 * m.nbody; i += 32) a.xpos[e * 3 * m.nbody + i] = c.xpos[i];
-  if (a.xquat) for (int i = lane; i < 4 * m.nbody; i += 32) a.xquat[e * 4 * m.nbody + i] = c.xquat[i];
-  if (a.subtree_com) for (int i = lane; i < 3 * m.nroot; i += 32) a.subtree_com[e * 3 * m.nroot + i] = c.com[i];
-  if (a.qfrc_actuator) for (int i = lane; i < m.nv; i += 32) a.qfrc_actuator[e * m.nv + i] = c.qfrc_act[i];
-  if (a.cinert) for (int i = lane; i < 10 * m.nbody; i += 32) a.cinert[e * 10 * m.nbody + i] = c.cinert[i];
-  if (a.cvel) for (int i = lane; i < 6 * m.nbody; i += 32) a.cvel[e * 6 * m.nbody + i] = c.cvel[i];
+  /* optional raw outputs that survive the solver phase */
   if (a.contact_dist && m.nefc) for (int i = lane; i < m.ncon; i += 32) a.contact_dist[e * m.ncon + i] = c.con_dist[i];
   if (a.qacc) RR_FOR_S { int i = lane + 32 * s; if (i < m.nv) a.qacc[e * m.nv + i] = c.qacc[s]; }
   prof<NS>(c, RR_PROF_EPILOGUE);
 }
 
-}  // namespace rr
+}  // namespace RR_NS
 
-#endif /* RR_KERNELS_INL_ */

@@ -140,6 +140,7 @@ inline void rr_host_model_build(RRHostModel &hm, const int32_t *dir, const int32
   /* ---- dofs + tree-sparse layout ---- */
   cpI(t_dof_bodyid, RR_FID(dof_bodyid));
   cpI(t_dof_rowadr, RR_FID(M_rowadr));
+  std::vector<int32_t> t_M_colind, t_M_rowid;
   cpI(t_M_colind, RR_FID(M_colind));
   cpF(t_dof_armature, RR_FID(dof_armature)); cpF(t_dof_damping, RR_FID(dof_damping));
   const int32_t *dofparent = B.I(RR_FID(dof_parentid)), *rownnz = B.I(RR_FID(M_rownnz));
@@ -160,6 +161,16 @@ inline void rr_host_model_build(RRHostModel &hm, const int32_t *dir, const int32
   for (int i = 0; i < nv; i++)
     for (int t = 0; t < rownnz[i]; t++) t_M_rowid[t_dof_rowadr[i] + t] = i;
   if (t_M_rowid.empty()) { t_M_rowid.push_back(0); t_M_colind.push_back(0); }
+  /* packed entry metadata (row | col << 8 | rowadr[col] << 16) and the triangular enumeration used by factor() */
+  if (nv > 255 || nM > 65535) throw std::runtime_error("NotImplemented: nv > 255");
+  t_M_meta.resize(t_M_colind.size());
+  for (size_t e = 0; e < t_M_colind.size(); e++)
+    t_M_meta[e] = nv ? (t_M_rowid[e] | (t_M_colind[e] << 8) | (t_dof_rowadr[t_M_colind[e]] << 16)) : 0;
+  {
+    int maxdep = 0;
+    for (int i = 0; i < nv; i++) maxdep = std::max(maxdep, t_dof_depth[i]);
+    if (maxdep > 63) throw std::runtime_error("NotImplemented: kinematic chains deeper than 63 dofs");
+  }
 
   /* ---- actuators ---- */
   const int32_t *ajnt = B.I(RR_FID(actuator_jntid));
@@ -264,40 +275,59 @@ inline void rr_host_model_build(RRHostModel &hm, const int32_t *dir, const int32
 #undef RR__X
   if (hm.ibuf.empty()) hm.ibuf.push_back(0);
   if (hm.fbuf.empty()) hm.fbuf.push_back(0.f);
+  padI();
+  padF();
 
-  /* ---- shared-memory layout ---- */
+  /* ---- shared-memory layout (see RRSmem) ---- */
   RRSmem &s = d.sm;
   int o = 0;
   auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };
   s.qpos = take(nq); s.qvel = take(nv); s.act = take(d.na); s.ctrl = take(nu); s.actdot = take(d.na);
-  s.xpos = take(3 * nb); s.xquat = take(4 * nb); s.com = take(3 * d.nroot);
-  s.cinert = take(10 * nb); s.cdof = take(6 * nv); s.cvel = take(6 * nb);
-  s.M = take(nM); s.LD = take(nM); s.Dinv = take(nv); s.vbuf = take(nv); s.qfrc_act = take(nv);
-  s.tmp = o;
-  int t0 = o, tmax = o;
-  /* mass-matrix phase */
-  o = t0; s.crb = take(10 * nb); s.fcrb = take(6 * nv); tmax = std::max(tmax, o);
-  /* rne phase */
-  o = t0; s.cacc = take(6 * nb); s.cfrc = take(6 * nb); tmax = std::max(tmax, o);
-  /* constraint + solver phase */
-  o = t0; s.con_dist = take(nc); s.con_pos = take(3 * nc); s.con_frame = take(9 * nc); s.con_J = take(nJ);
-  s.row_D = take(d.nefc); s.row_aref = take(d.nefc); s.row_Jaref = take(d.nefc); s.row_jv = take(d.nefc);
-  s.row_id = take(d.nefc); s.cact = take(nc); tmax = std::max(tmax, o);
-  s.total = tmax;
+  s.com = take(3 * d.nroot); s.vbuf = take(nv); s.Dinv = take(nv); s.xq1 = take(4);
+  s.M = take(nM); s.LD = take(nM);
+  s.xpos = take(3 * nb); s.xquat = take(4 * nb); s.cdof = take(6 * nv);
+  const int c0 = o;
+  /* C1 */
+  s.cinert = take(10 * nb); s.qfrc_act = take(nv);
+  const int c1b = o;
+  s.cvel = take(6 * nb); s.cacc = take(6 * nb); s.cfrc = s.cacc; /* cfrc is computed in place over cacc */
+  int c1_end = o;
+  o = c1b; s.crb = take(10 * nb); s.fcrb = s.crb;
+  c1_end = std::max(c1_end, o);
+  /* C2: fixed part, then split what is left between Jacobian blocks and rows (5 arrays of capR) */
+  o = c0;
+  s.con_dist = take(nc); s.con_pos = take(3 * nc); s.con_frame = take(9 * nc); s.cact = take(nc); s.cmeta = take(4 * nc);
+  int avail = c1_end - o;
+  int capR = std::min(d.nefc, 96) & ~3;
+  if (capR < 4) capR = 4;
+  int capJ = avail - 5 * capR;
+  if (capJ < 3 * 40) { /* tiny models: grow the region instead */
+    capJ = std::min(nJ, 3 * 40 * 4);
+    capJ = (capJ + 3) & ~3;
+  }
+  capJ = std::min(capJ & ~3, (nJ + 3) & ~3);
+  if (capJ < 4) capJ = 4;
+  s.capJ = capJ; s.capR = capR;
+  s.con_J = take(capJ); s.row_D = take(5 * capR);
+  s.total = std::max(c1_end, o);
 
   hm.obs_dim = nq + nv + 10 * (nb - 1) + 6 * (nb - 1) + nv + 3; /* Rodent_Env_Brax.py:149-158 */
 }
 
-/* Point the table pointers of `dev` at copies of ibuf / fbuf living at ibase / fbase. */
+/* Fill the table offsets of `dev` and point it at copies of ibuf / fbuf living at ibase / fbase. */
 inline void rr_host_model_bind(const RRHostModel &hm, RRModelDev &dev, const int32_t *ibase, const float *fbase) {
   int k = 0;
-#define RR__X(n) dev.n = ibase + hm.ioff[k++];
+#define RR__X(n) dev.o_##n = hm.ioff[k++];
   RR_DEV_INT_TABLES(RR__X)
 #undef RR__X
   k = 0;
-#define RR__X(n) dev.n = fbase + hm.foff[k++];
+#define RR__X(n) dev.o_##n = hm.foff[k++];
   RR_DEV_FLOAT_TABLES(RR__X)
 #undef RR__X
+  dev.ibuf = ibase;
+  dev.fbuf = fbase;
+  dev.ni = (int)hm.ibuf.size();
+  dev.nf = (int)hm.fbuf.size();
 }
 
 #endif /* RR_MODEL_BUILD_H_ */

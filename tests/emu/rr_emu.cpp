@@ -105,8 +105,10 @@ static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 #define RR_DEV static inline
 #define RR_HOSTDEV static inline
 #define RR_DEV_MEMBER inline
+#define RR_DEV_NOINLINE static
 #define RR_LDG(p) (*(p))
 #define RR_CLOCK() 0LL
+#define RR_CTA_SYNC() ((void)0)
 
 #include "../../brax_rodent_run_b200/csrc/rr_kernels.inl"
 
@@ -118,19 +120,23 @@ static void rrb_free(void *p) { free(p); }
 static int rrb_h2d(void *dst, const void *src, size_t bytes, void *) { memcpy(dst, src, bytes); return 0; }
 static int rrb_d2h(void *dst, const void *src, size_t bytes, void *) { memcpy(dst, src, bytes); return 0; }
 static int rrb_sync(void *) { return 0; }
+static int rrb_num_slots() { return 1; }
 
-struct EmuJob { const RRModelDev *m; const RRStepArgs *a; int env; float *sm; };
+struct EmuJob { const RRModelDev *m; const RRStepArgs *a; int env; float *sm; const int32_t *ti; const float *tf; };
 template <int NS>
 static void emu_lane(int lane, void *arg) {
   EmuJob *j = (EmuJob *)arg;
-  rr::env_run<NS>(*j->m, *j->a, j->env, j->sm, lane);
+  rr::env_run<NS>(*j->m, *j->a, j->env, 0, j->sm, j->ti, j->tf, lane);
 }
 static int rrb_launch_step(const RRModelDev &m, const RRStepArgs &a, void *) {
   std::vector<float> sm((size_t)m.sm.total + 16);
   for (int env = 0; env < a.B; env++) {
     /* poison shared memory so that reads of unwritten slots show up as NaN */
     for (auto &x : sm) x = NAN;
-    EmuJob j{&m, &a, env, sm.data()};
+    /* "shared memory" copies of the tables, as the CUDA kernel stages them */
+    std::vector<int32_t> ti(m.ibuf, m.ibuf + m.ni);
+    std::vector<float> tf(m.fbuf, m.fbuf + m.nf);
+    EmuJob j{&m, &a, env, sm.data(), ti.data(), tf.data()};
     emu::run_warp(m.nv <= 96 ? emu_lane<3> : emu_lane<5>, &j);
   }
   return 0;
