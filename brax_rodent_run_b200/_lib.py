@@ -46,7 +46,7 @@ _libs = {}
 
 def load(path: Optional[str] = None):
     """Load (once) and type the shared library.  `path=None` is the CUDA product library."""
-    path = path or LIB_PATH
+    path = path or os.environ.get("RR_B200_LIB") or LIB_PATH  # RR_B200_LIB: developer hook to A/B kernel builds
     if path in _libs:
         return _libs[path]
     if not os.path.exists(path):

@@ -48,6 +48,13 @@
 #ifndef RR_CTA_SYNC
 #define RR_CTA_SYNC() __syncthreads()
 #endif
+#ifndef RR_MV_RECURRENCE
+#define RR_MV_RECURRENCE 1
+#endif
+#ifndef RR_SYNC_LEVEL
+#define RR_SYNC_LEVEL 2 /* 1: per substep; 2: + before each factorisation and the collision phase; 3: + per CG iteration */
+#endif
+#define RR_CTA_SYNC_AT(level) do { if (RR_SYNC_LEVEL >= (level)) RR_CTA_SYNC(); } while (0)
 
 #define RR_FULL 0xffffffffu
 #define RR_MINVAL 1e-15f
@@ -1168,26 +1175,36 @@ RR_DEV void solve_constraints(Ctx<NS> &c) {
   }
   prof<NS>(c, RR_PROF_SOLVE_INIT);
   int niter = 0;
-  bool first = true;
-  for (;;) {
+  bool first = true, finished = false;
+  /* fixed trip count (iterations + 1 gradient updates at most) so that the CTA-wide rendezvous below stays matched
+   * across warps; a warp whose solve has converged idles through the remaining trips */
+#pragma unroll 1
+  for (int trip = 0; trip <= m.iterations; trip++) {
+    RR_CTA_SYNC_AT(3);
+    if (finished) continue;
     float prev_grad[NS], prev_Mgrad[NS];
     if (!first) {
       if (m.iterations != 1) {
         float improvement = (prev_cost - cost) * scale;
         float gradient = sqrtf(vdot<NS>(grad, grad)) * scale;
-        if (niter >= m.iterations || improvement < m.tolerance || gradient < m.tolerance) break;
+        if (niter >= m.iterations || improvement < m.tolerance || gradient < m.tolerance) { finished = true; continue; }
       } else if (niter >= 1) {
-        break;
+        finished = true;
+        continue;
       }
       /* ---- linesearch ---- */
       float smag = sqrtf(vdot<NS>(search, search)) * m.meaninertia * nvf;
       float gtol = m.tolerance * m.ls_tolerance * smag;
       /* mv = M search.  search = -Mgrad + beta search_prev with M Mgrad = grad (Mgrad is the LD solve of grad), so
        * mv = -grad + beta mv_prev: the same vector MJX gets from mul_m(search), without the product. */
+#if RR_MV_RECURRENCE
       RR_FOR_S mv[s] = -grad[s] + beta * mv[s];
       __syncwarp();
       vstore<NS>(c, search, c.vbuf);
       __syncwarp();
+#else
+      mul_m<NS>(c, mv, search); /* leaves search staged in vbuf */
+#endif
       mul_j<NS>(c, c.row_jv);
       float g0 = gauss, g1 = 0.f, g2 = 0.f;
       RR_FOR_S { g1 += search[s] * (Ma[s] - c.qfrc_smooth[s]); g2 += search[s] * mv[s]; }
@@ -1317,7 +1334,7 @@ template <int NS>
 RR_DEV void substep(Ctx<NS> &c, bool integrate, float &time) {
   const RRModelDev &m = c.m;
   const float dt = m.timestep;
-  RR_CTA_SYNC();
+  RR_CTA_SYNC_AT(1);
   kinematics<NS>(c);
   prof<NS>(c, RR_PROF_FK);
   com_pos<NS>(c);
@@ -1339,7 +1356,7 @@ RR_DEV void substep(Ctx<NS> &c, bool integrate, float &time) {
   }
   if (c.last_substep) forward_outputs<NS>(c);
   for (int pass = 0; pass < 2; pass++) {
-    RR_CTA_SYNC();
+    RR_CTA_SYNC_AT(2);
     factor<NS>(c, pass ? dt : 0.f);
     float x[NS];
     RR_FOR_S x[s] = pass ? c.qfrc_smooth[s] + c.qfrc_constraint[s] : c.qfrc_smooth[s];
@@ -1353,7 +1370,7 @@ RR_DEV void substep(Ctx<NS> &c, bool integrate, float &time) {
       if (m.nefc == 0) {
         RR_FOR_S { c.qacc[s] = c.qacc_smooth[s]; c.qfrc_constraint[s] = 0.f; }
       } else {
-        RR_CTA_SYNC();
+        RR_CTA_SYNC_AT(2);
         collision<NS>(c);
         prof<NS>(c, RR_PROF_COLLIDE);
         make_constraint<NS>(c);
