@@ -1,0 +1,343 @@
+"""PPO on the B200 rodent env -- the torch counterpart of the `ppo.train` call in brax_rodent_run_ppo.py:97-114,200.
+
+Follows brax 0.10.x `brax.training.agents.ppo` (restated from its published algorithm, brax is
+not installable here): policy MLP (32,)*4 -> 2*nu, value MLP (256,)*5 -> 1, swish, lecun-uniform init; tanh-normal
+policy with scale = softplus(.) + 1e-3; running mean/std observation normaliser updated once per training step; GAE
+(the rr_gae CUDA kernel); clipped surrogate (eps 0.3) + 0.25 * value error^2 - entropy_cost * entropy; Adam; per
+training step `batch_size * num_minibatches / num_envs` unrolls of `unroll_length` env steps, then
+`num_updates_per_batch` epochs over `num_minibatches` shuffled minibatches.
+
+Multi-GPU: one process per GPU (torchrun), environments sharded per rank with no communication during rollout; NCCL
+all-reduce only for the flat gradient (one bucket per minibatch), the normaliser moments (once per training step)
+and the metrics -- the `lax.pmean / psum` calls of brax's pmap'd train step.
+"""
+from __future__ import annotations
+
+import ctypes
+import dataclasses
+import math
+import time
+from typing import Callable, Dict, Optional
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib
+from .env import Rodent, State
+
+
+@dataclasses.dataclass
+class PPOConfig:
+    """Defaults = the arguments of train_fn in brax_rodent_run_ppo.py:97-114 plus brax's own defaults."""
+    num_timesteps: int = 10_000_000
+    episode_length: int = 1000
+    num_envs: int = 2048            # per process
+    batch_size: int = 512           # per process
+    num_minibatches: int = 64
+    unroll_length: int = 10
+    num_updates_per_batch: int = 8
+    learning_rate: float = 3e-4
+    discounting: float = 0.97
+    gae_lambda: float = 0.95
+    clipping_epsilon: float = 0.3
+    entropy_cost: float = 1e-3
+    reward_scaling: float = 1.0
+    normalize_observations: bool = True
+    normalize_advantage: bool = True
+    num_evals: int = 1
+    num_eval_envs: int = 128
+    deterministic_eval: bool = False
+    seed: int = 0
+    policy_hidden: tuple = (32, 32, 32, 32)
+    value_hidden: tuple = (256, 256, 256, 256, 256)
+
+
+def _mlp(sizes, out) -> nn.Sequential:
+    layers, last = [], sizes[0]
+    for h in sizes[1:]:
+        layers += [nn.Linear(last, h), nn.SiLU()]
+        last = h
+    layers.append(nn.Linear(last, out))
+    net = nn.Sequential(*layers)
+    for mod in net:
+        if isinstance(mod, nn.Linear):  # jax.nn.initializers.lecun_uniform, zero bias
+            bound = math.sqrt(3.0 / mod.in_features)
+            nn.init.uniform_(mod.weight, -bound, bound)
+            nn.init.zeros_(mod.bias)
+    return net
+
+
+class RunningStats:
+    """brax.training.acme.running_statistics: count / mean / summed_variance / std, updated with (optionally
+    all-reduced) batch moments."""
+
+    def __init__(self, size: int, device):
+        self.count = torch.zeros((), device=device, dtype=torch.float64)
+        self.mean = torch.zeros(size, device=device)
+        self.summed_variance = torch.zeros(size, device=device)
+        self.std = torch.ones(size, device=device)
+
+    def update(self, batch: torch.Tensor, distributed: bool = False, std_min=1e-6, std_max=1e6) -> None:
+        batch = batch.reshape(-1, batch.shape[-1])
+        n = torch.tensor(float(batch.shape[0]), device=batch.device, dtype=torch.float64)
+        diff_old = batch - self.mean
+        s1 = diff_old.sum(0)
+        if distributed:
+            dist.all_reduce(n)
+            dist.all_reduce(s1)
+        count = self.count + n
+        mean = self.mean + s1 / count.float()
+        s2 = (diff_old * (batch - mean)).sum(0)
+        if distributed:
+            dist.all_reduce(s2)
+        self.summed_variance = self.summed_variance + s2
+        self.count, self.mean = count, mean
+        self.std = torch.sqrt(self.summed_variance / count.float()).clamp(std_min, std_max)
+
+    def normalize(self, x: torch.Tensor) -> torch.Tensor:
+        return (x - self.mean) / self.std
+
+    def state_dict(self):
+        return dict(count=self.count, mean=self.mean, summed_variance=self.summed_variance, std=self.std)
+
+    def load_state_dict(self, d):
+        self.count, self.mean, self.summed_variance, self.std = d["count"], d["mean"], d["summed_variance"], d["std"]
+
+
+_LOG2 = math.log(2.0)
+
+
+def tanh_normal_sample(logits: torch.Tensor, gen: Optional[torch.Generator] = None):
+    """NormalTanhDistribution: returns (action, raw_action, log_prob)."""
+    loc, scale = logits.chunk(2, dim=-1)
+    scale = F.softplus(scale) + 1e-3
+    eps = torch.randn(loc.shape, device=loc.device, generator=gen)
+    raw = loc + scale * eps
+    return torch.tanh(raw), raw, tanh_normal_log_prob(logits, raw)
+
+
+def tanh_normal_log_prob(logits: torch.Tensor, raw: torch.Tensor) -> torch.Tensor:
+    loc, scale = logits.chunk(2, dim=-1)
+    scale = F.softplus(scale) + 1e-3
+    lp = -0.5 * ((raw - loc) / scale) ** 2 - torch.log(scale) - 0.5 * math.log(2 * math.pi)
+    lp = lp - 2.0 * (_LOG2 - raw - F.softplus(-2.0 * raw))  # tanh log-det-jacobian
+    return lp.sum(-1)
+
+
+def tanh_normal_entropy(logits: torch.Tensor, gen: Optional[torch.Generator] = None) -> torch.Tensor:
+    loc, scale = logits.chunk(2, dim=-1)
+    scale = F.softplus(scale) + 1e-3
+    ent = 0.5 + 0.5 * math.log(2 * math.pi) + torch.log(scale)
+    raw = loc + scale * torch.randn(loc.shape, device=loc.device, generator=gen)
+    ent = ent + 2.0 * (_LOG2 - raw - F.softplus(-2.0 * raw))
+    return ent.sum(-1)
+
+
+def compute_gae(L, truncation, termination, rewards, values, bootstrap, lambda_, discount):
+    """ppo.losses.compute_gae on the rr_gae kernel; inputs time-major [T, B] contiguous CUDA tensors."""
+    T, B = rewards.shape
+    vs, adv = torch.empty_like(rewards), torch.empty_like(rewards)
+    p = lambda x: ctypes.c_void_p(x.data_ptr())
+    stream = ctypes.c_void_p(torch.cuda.current_stream(rewards.device).cuda_stream) if rewards.is_cuda else None
+    _lib.check(L, L.rr_gae(p(rewards.contiguous()), p(values.contiguous()), p(bootstrap.contiguous()), p(termination.contiguous()),
+                           p(truncation.contiguous()), T, B, discount, lambda_, p(vs), p(adv), stream))
+    return vs, adv
+
+
+class PPO:
+    def __init__(self, env: Rodent, cfg: PPOConfig):
+        self.env, self.cfg = env, cfg
+        self.device = env.device
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        assert (cfg.batch_size * cfg.num_minibatches) % cfg.num_envs == 0, "batch_size * num_minibatches % num_envs"
+        assert env.num_envs == cfg.num_envs
+        torch.manual_seed(cfg.seed)  # identical initial parameters on every rank
+        obs, act = env.observation_size, env.action_size
+        self.policy = _mlp((obs,) + tuple(cfg.policy_hidden), 2 * act).to(self.device)
+        self.value = _mlp((obs,) + tuple(cfg.value_hidden), 1).to(self.device)
+        self.params = list(self.policy.parameters()) + list(self.value.parameters())
+        self.opt = torch.optim.Adam(self.params, lr=cfg.learning_rate, eps=1e-8)
+        self.normalizer = RunningStats(obs, self.device)
+        self.gen = torch.Generator(device=self.device)
+        self.gen.manual_seed(cfg.seed * 1000 + 17 + self.rank)
+        self.env_steps = 0
+        self._flat_grad = None
+
+    # ---- acting -----------------------------------------------------------------------------------------------------
+    def _norm(self, obs):
+        return self.normalizer.normalize(obs) if self.cfg.normalize_observations else obs
+
+    @torch.no_grad()
+    def act(self, obs, deterministic=False):
+        logits = self.policy(self._norm(obs))
+        if deterministic:
+            loc = logits.chunk(2, dim=-1)[0]
+            return torch.tanh(loc), loc, torch.zeros(obs.shape[0], device=obs.device)
+        return tanh_normal_sample(logits, self.gen)
+
+    @torch.no_grad()
+    def unroll(self, state: State):
+        """acting.generate_unroll: `unroll_length` policy + env steps; returns (state, transitions time-major)."""
+        T = self.cfg.unroll_length
+        obs, raw, logp, rew, disc, trunc = [], [], [], [], [], []
+        for _ in range(T):
+            action, raw_a, lp = self.act(state.obs)
+            obs.append(state.obs)
+            state = self.env.step(state, action)
+            raw.append(raw_a); logp.append(lp); rew.append(state.reward)
+            disc.append(1.0 - state.done)
+            trunc.append(state.info["truncation"])
+        data = dict(observation=torch.stack(obs), raw_action=torch.stack(raw), log_prob=torch.stack(logp),
+                    reward=torch.stack(rew), discount=torch.stack(disc), truncation=torch.stack(trunc),
+                    next_observation_last=state.obs)
+        return state, data
+
+    # ---- learning ---------------------------------------------------------------------------------------------------
+    def loss(self, mb: Dict[str, torch.Tensor]):
+        cfg = self.cfg
+        obs = self._norm(mb["observation"])                      # [T, b, obs]
+        logits = self.policy(obs)
+        baseline = self.value(obs).squeeze(-1)
+        with torch.no_grad():
+            bootstrap = self.value(self._norm(mb["next_observation_last"])).squeeze(-1)
+            rewards = mb["reward"] * cfg.reward_scaling
+            truncation = mb["truncation"]
+            termination = (1 - mb["discount"]) * (1 - truncation)
+            vs, adv = compute_gae(self.env._L, truncation, termination, rewards, baseline.detach(), bootstrap, cfg.gae_lambda,
+                                  cfg.discounting)
+            if cfg.normalize_advantage:
+                adv = (adv - adv.mean()) / (adv.std(unbiased=False) + 1e-8)
+        target_lp = tanh_normal_log_prob(logits, mb["raw_action"])
+        rho = torch.exp(target_lp - mb["log_prob"])
+        s1, s2 = rho * adv, rho.clamp(1 - cfg.clipping_epsilon, 1 + cfg.clipping_epsilon) * adv
+        policy_loss = -torch.min(s1, s2).mean()
+        v_loss = ((vs - baseline) ** 2).mean() * 0.5 * 0.5
+        entropy = tanh_normal_entropy(logits, self.gen).mean()
+        entropy_loss = -cfg.entropy_cost * entropy
+        total = policy_loss + v_loss + entropy_loss
+        return total, dict(total_loss=total.detach(), policy_loss=policy_loss.detach(), v_loss=v_loss.detach(),
+                           entropy_loss=entropy_loss.detach())
+
+    def _allreduce_grads(self):
+        """lax.pmean(grads): one flat fp32 bucket (2.53 MB for the rodent networks) per minibatch over NCCL."""
+        if self.world == 1:
+            return
+        grads = [p.grad for p in self.params]
+        if self._flat_grad is None:
+            self._flat_grad = torch.empty(sum(g.numel() for g in grads), device=self.device)
+        torch.cat([g.reshape(-1) for g in grads], out=self._flat_grad)
+        dist.all_reduce(self._flat_grad)
+        self._flat_grad.div_(self.world)
+        off = 0
+        for g in grads:
+            g.copy_(self._flat_grad[off:off + g.numel()].view_as(g))
+            off += g.numel()
+
+    def training_step(self, state: State):
+        cfg = self.cfg
+        n_unroll = cfg.batch_size * cfg.num_minibatches // cfg.num_envs
+        chunks = []
+        for _ in range(n_unroll):
+            state, data = self.unroll(state)
+            chunks.append(data)
+        # [T, n_unroll * num_envs, ...]: the "batch" axis that brax shuffles is (unroll, env)
+        data = {k: torch.cat([c[k] for c in chunks], dim=1 if k != "next_observation_last" else 0) for k in chunks[0]}
+        if cfg.normalize_observations:
+            self.normalizer.update(data["observation"], distributed=self.world > 1)
+        nb = data["reward"].shape[1]
+        metrics = {}
+        for _ in range(cfg.num_updates_per_batch):
+            perm = torch.randperm(nb, device=self.device, generator=self.gen)
+            for i in range(cfg.num_minibatches):
+                idx = perm[i * cfg.batch_size:(i + 1) * cfg.batch_size]
+                mb = {k: (v[:, idx] if k != "next_observation_last" else v[idx]) for k, v in data.items()}
+                total, metrics = self.loss(mb)
+                self.opt.zero_grad(set_to_none=False)
+                total.backward()
+                self._allreduce_grads()
+                self.opt.step()
+        self.env_steps += n_unroll * cfg.unroll_length * cfg.num_envs * self.world
+        return state, metrics
+
+    # ---- evaluation (acting.Evaluator) ---------------------------------------------------------------------------------
+    @torch.no_grad()
+    def evaluate(self, eval_env: Rodent, seed: int = 1) -> Dict[str, float]:
+        state = eval_env.reset(seed)
+        ret = torch.zeros(eval_env.num_envs, device=self.device)
+        alive = torch.ones_like(ret)
+        length = torch.zeros_like(ret)
+        sums = {k: torch.zeros_like(ret) for k in ("pos_reward", "reward_quadctrl", "reward_alive")}
+        for _ in range(self.cfg.episode_length):
+            action, _, _ = self.act(state.obs, deterministic=self.cfg.deterministic_eval)
+            state = eval_env.step(state, action)
+            ret += state.reward * alive
+            length += alive
+            for k in sums:
+                sums[k] += state.metrics[k] * alive
+            alive = alive * (1 - state.done)
+        out = {"eval/episode_reward": ret.mean(), "eval/avg_episode_length": length.mean()}
+        out.update({f"eval/episode_{k}": v.mean() for k, v in sums.items()})
+        if self.world > 1:
+            for v in out.values():
+                dist.all_reduce(v)
+                v.div_(self.world)
+        return {k: float(v) for k, v in out.items()}
+
+    # ---- checkpointing (brax model.save_params saves (normalizer, policy); we also keep value + optimiser) ---------------
+    def state_dict(self):
+        return dict(policy=self.policy.state_dict(), value=self.value.state_dict(), normalizer=self.normalizer.state_dict(),
+                    optimizer=self.opt.state_dict(), env_steps=self.env_steps)
+
+    def load_state_dict(self, d):
+        self.policy.load_state_dict(d["policy"]); self.value.load_state_dict(d["value"])
+        self.normalizer.load_state_dict(d["normalizer"]); self.opt.load_state_dict(d["optimizer"])
+        self.env_steps = d["env_steps"]
+
+    def export_brax_params(self):
+        """(normalizer, policy) in the flax naming brax pickles (`hidden_i` / kernel [in, out] / bias), as numpy."""
+        def mlp(net):
+            lin = [m for m in net if isinstance(m, nn.Linear)]
+            return {"params": {f"hidden_{i}": {"kernel": l.weight.detach().t().cpu().numpy(), "bias": l.bias.detach().cpu().numpy()}
+                               for i, l in enumerate(lin)}}
+        n = self.normalizer
+        norm = dict(count=float(n.count), mean=n.mean.cpu().numpy(), summed_variance=n.summed_variance.cpu().numpy(),
+                    std=n.std.cpu().numpy())
+        return norm, mlp(self.policy)
+
+
+def train(environment: Rodent, cfg: PPOConfig, progress_fn: Callable[[int, Dict], None] = lambda *a: None,
+          policy_params_fn: Callable = lambda *a: None, eval_env: Optional[Rodent] = None):
+    """ppo.train(environment=env, progress_fn=..., policy_params_fn=...) (brax_rodent_run_ppo.py:200-202).
+    Returns (make_inference_fn, params, metrics) like brax."""
+    agent = PPO(environment.wrap_for_training(cfg.episode_length), cfg)
+    steps_per_train = cfg.batch_size * cfg.num_minibatches * cfg.unroll_length * agent.world
+    num_train = max(1, -(-cfg.num_timesteps // steps_per_train))
+    per_eval = max(1, num_train // max(cfg.num_evals, 1))
+    state = environment.reset(cfg.seed + agent.rank)
+    metrics: Dict[str, float] = {}
+    t0 = time.time()
+    for it in range(num_train):
+        state, m = agent.training_step(state)
+        if (it + 1) % per_eval == 0 or it == num_train - 1:
+            if agent.device.type == "cuda":
+                torch.cuda.synchronize(agent.device)
+            metrics = {f"training/{k}": float(v) for k, v in m.items()}
+            metrics["training/sps"] = agent.env_steps / (time.time() - t0)
+            metrics["training/walltime"] = time.time() - t0
+            if eval_env is not None:
+                metrics.update(agent.evaluate(eval_env))
+            if agent.rank == 0:
+                progress_fn(agent.env_steps, metrics)
+                policy_params_fn(agent.env_steps, agent.make_inference_fn if hasattr(agent, "make_inference_fn") else None,
+                                 agent.export_brax_params())
+
+    def make_inference_fn(params=None, deterministic=False):
+        def policy(obs, rng=None):
+            action, raw, lp = agent.act(obs, deterministic)
+            return action, {"log_prob": lp, "raw_action": raw}
+        return policy
+
+    return make_inference_fn, agent, metrics
