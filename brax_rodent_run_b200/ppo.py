@@ -94,7 +94,7 @@ class RunningStats:
             dist.all_reduce(s2)
         self.summed_variance = self.summed_variance + s2
         self.count, self.mean = count, mean
-        self.std = torch.sqrt(self.summed_variance / count.float()).clamp(std_min, std_max)
+        self.std = torch.sqrt((self.summed_variance / count.float()).clamp_min(0.0)).clamp(std_min, std_max)
 
     def normalize(self, x: torch.Tensor) -> torch.Tensor:
         return (x - self.mean) / self.std
