@@ -114,17 +114,20 @@ static int rrb_launch_ns(const RRModelDev &m, const RRStepArgs &a, void *stream)
   int wpb = (int)((RR_SMEM_MAX - tables) / per_env);
   if (wpb > RR_MAX_WPB) wpb = RR_MAX_WPB;
   size_t smem = tables + per_env * wpb;
-  static thread_local int n_sm = 0;
-  static thread_local bool configured = false;
-  if (!configured) {
-    int dev = 0;
-    if (rrb_check(cudaGetDevice(&dev), "cudaGetDevice") ||
-        rrb_check(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev), "cudaDeviceGetAttribute") ||
+  /* per-device one-time setup (SM count, opt-in shared memory) */
+  static int n_sm_dev[64] = {0};
+  int dev = 0;
+  if (rrb_check(cudaGetDevice(&dev), "cudaGetDevice")) return 1;
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (n_sm_dev[dev] == 0) {
+    int n = 0;
+    if (rrb_check(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev), "cudaDeviceGetAttribute") ||
         rrb_check(cudaFuncSetAttribute(rr_step_kernel<NS, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, RR_SMEM_MAX),
                   "cudaFuncSetAttribute(smem)"))
       return 1;
-    configured = true;
+    n_sm_dev[dev] = n;
   }
+  const int n_sm = n_sm_dev[dev];
   int grid = (a.B + wpb - 1) / wpb;
   if (grid > n_sm) grid = n_sm;
   rr_step_kernel<NS, DBG><<<grid, 32 * wpb, smem, (cudaStream_t)stream>>>(m, a);

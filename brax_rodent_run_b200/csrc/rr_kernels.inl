@@ -503,90 +503,117 @@ RR_DEV void crb_and_mass_matrix(Ctx<NS> &c) {
 template <int NS>
 RR_DEV void factor(Ctx<NS> &c, float diag_scale) {
   const RRModelDev &m = c.m;
+  float2 *stage = reinterpret_cast<float2 *>(c.cacc); /* (w_j, rowadr_j) per descendant; cacc is dead in both passes */
   __syncwarp();
 #pragma unroll 1
   for (int k = m.nv - 1; k >= 0; k--) {
     const int mk = RI(dof_depth, k), adr = RI(dof_rowadr, k), nd = RI(dof_ndesc, k);
-    const int s0 = c.lane, s1 = c.lane + 32;
-    float acc0 = 0.f, acc1 = 0.f;
-    if (s0 <= mk) acc0 = c.M[adr + s0];
-    if (s1 <= mk) acc1 = c.M[adr + s1];
-    if (diag_scale != 0.f) {
-      float dd = diag_scale * RF(dof_damping, k);
-      if (s0 == mk) acc0 += dd;
-      if (s1 == mk) acc1 += dd;
-    }
-    if (nd > 0) {
-      for (int jj = c.lane; jj < nd; jj += 32) {
-        int j = k + 1 + jj, rj = RI(dof_rowadr, j);
-        c.vbuf[jj] = c.LD[rj + mk] * c.LD[rj + RI(dof_depth, j)];
+    if (mk < 32) {
+      /* short rows leave lanes idle: split the descendants over G = 32 / W lane groups (W = row width rounded up to a
+       * power of two) and add the partial sums with shuffles */
+      const int lw = RI(dof_log2w, k), W = 1 << lw, G = 32 >> lw;
+      const int s0 = c.lane & (W - 1), g = c.lane >> lw;
+      const bool on = s0 <= mk;
+      float acc = 0.f;
+      if (g == 0 && on) {
+        acc = c.M[adr + s0];
+        if (s0 == mk && diag_scale != 0.f) acc += diag_scale * RF(dof_damping, k);
       }
-      __syncwarp();
-      if (mk < 32) {
-#pragma unroll 4
-        for (int jj = 0; jj < nd; jj++) {
-          const int rj = RI(dof_rowadr, k + 1 + jj);
-          const float w = c.vbuf[jj];
-          if (s0 <= mk) acc0 -= w * c.LD[rj + s0];
+      if (nd > 0) {
+        for (int jj = c.lane; jj < nd; jj += 32) {
+          int j = k + 1 + jj, rj = RI(dof_rowadr, j);
+          stage[jj] = make_float2(c.LD[rj + mk] * c.LD[rj + RI(dof_depth, j)], __int_as_float(rj));
         }
-      } else {
+        __syncwarp();
+#pragma unroll 4
+        for (int jj = g; jj < nd; jj += G) {
+          const float2 wr = stage[jj];
+          if (on) acc -= wr.x * c.LD[__float_as_int(wr.y) + s0];
+        }
+        for (int o = W; o < 32; o <<= 1) acc += __shfl_xor_sync(RR_FULL, acc, o);
+      }
+      const float dk = __shfl_sync(RR_FULL, acc, mk);
+      const float inv = 1.f / dk;
+      if (g == 0 && s0 < mk) c.LD[adr + s0] = acc * inv;
+      if (c.lane == 0) { c.LD[adr + mk] = dk; c.Dinv[k] = inv; }
+    } else {
+      /* rows of 33 .. 64 entries: two registers per lane */
+      const int s0 = c.lane, s1 = c.lane + 32;
+      float acc0 = c.M[adr + s0], acc1 = 0.f;
+      if (s1 <= mk) acc1 = c.M[adr + s1];
+      if (s1 == mk && diag_scale != 0.f) acc1 += diag_scale * RF(dof_damping, k);
+      if (nd > 0) {
+        for (int jj = c.lane; jj < nd; jj += 32) {
+          int j = k + 1 + jj, rj = RI(dof_rowadr, j);
+          stage[jj] = make_float2(c.LD[rj + mk] * c.LD[rj + RI(dof_depth, j)], __int_as_float(rj));
+        }
+        __syncwarp();
 #pragma unroll 2
         for (int jj = 0; jj < nd; jj++) {
-          const int rj = RI(dof_rowadr, k + 1 + jj);
-          const float w = c.vbuf[jj];
-          acc0 -= w * c.LD[rj + s0];
-          if (s1 <= mk) acc1 -= w * c.LD[rj + s1];
+          const float2 wr = stage[jj];
+          const int rj = __float_as_int(wr.y);
+          acc0 -= wr.x * c.LD[rj + s0];
+          if (s1 <= mk) acc1 -= wr.x * c.LD[rj + s1];
         }
       }
+      const float dk = __shfl_sync(RR_FULL, acc1, mk & 31);
+      const float inv = 1.f / dk;
+      c.LD[adr + s0] = acc0 * inv;
+      if (s1 < mk) c.LD[adr + s1] = acc1 * inv;
+      if (c.lane == 0) { c.LD[adr + mk] = dk; c.Dinv[k] = inv; }
     }
-    /* D_k sits in lane mk (or mk - 32 of the second register) */
-    const float dk = __shfl_sync(RR_FULL, mk < 32 ? acc0 : acc1, mk & 31);
-    const float inv = 1.f / dk;
-    if (s0 < mk) c.LD[adr + s0] = acc0 * inv;
-    if (s1 < mk) c.LD[adr + s1] = acc1 * inv;
-    if (c.lane == 0) { c.LD[adr + mk] = dk; c.Dinv[k] = inv; }
     __syncwarp();
   }
   RR_FOR_S { int i = c.lane + 32 * s; c.dinv[s] = i < m.nv ? c.Dinv[i] : 0.f; }
 }
 
-/* x <- (L D L')^-1 x with x distributed over lanes (dof i = lane + 32 s); pure register / shuffle solve.
- * Per step one value and its row metadata are broadcast from the owning lane; L(i, j) sits at rowadr[i] + depth[j]. */
+/* x <- (L' D L)^-1 x with x distributed over lanes (dof i = lane + 32 s); pure register / shuffle solve.
+ * L(i, j) sits at rowadr[i] + depth[j].  Both substitutions follow a host-built schedule (rr_model_build.h) that issues
+ * up to two mutually independent dofs (different branches of the tree) per step, critical path first: the tail chain
+ * (24 dofs) + trunk (12) bound the step count at about nv / 2, which halves the dependent shuffle -> FMA chain. */
 template <int NS>
 RR_DEV void solve_ld(Ctx<NS> &c, float (&x)[NS]) {
-  const int nv = c.m.nv;
-  /* backward: x <- L^-T x, leaves to root */
-#pragma unroll
-  for (int si = NS - 1; si >= 0; si--) {
-    const int top = (nv - 32 * si) < 32 ? (nv - 32 * si) : 32;
-    for (int src = top - 1; src >= 0; src--) {
-      const int i = 32 * si + src;
-      const int depi = __shfl_sync(RR_FULL, c.dep[si], src);
-      if (depi == 0) continue;
-      const float xi = __shfl_sync(RR_FULL, x[si], src);
-      const int adr = __shfl_sync(RR_FULL, c.radr[si], src);
-#pragma unroll
-      for (int s = 0; s <= si; s++) {
+  const RRModelDev &m = c.m;
+  /* backward: x <- L^-T x, leaves to root; step dof i updates its ancestors j: (unsigned)(i - j - 1) < ndesc[j] */
+#pragma unroll 4
+  for (int st = 0; st < m.nsched_back; st++) {
+    const int e = RI(sched_back, st), ia = e & 255, ib = (e >> 8) & 255;
+    const float xa = __shfl_sync(RR_FULL, vselect<NS>(x, ia >> 5), ia & 31);
+    const int adra = RI(dof_rowadr, ia);
+    if (ib != 255) {
+      const float xb = __shfl_sync(RR_FULL, vselect<NS>(x, ib >> 5), ib & 31);
+      const int adrb = RI(dof_rowadr, ib);
+      RR_FOR_S {
         const int j = c.lane + 32 * s;
-        if (j < i && i <= j + c.nd[s]) x[s] -= c.LD[adr + c.dep[s]] * xi;
+        if ((unsigned)(ia - 1 - j) < (unsigned)c.nd[s]) x[s] -= c.LD[adra + c.dep[s]] * xa;
+        if ((unsigned)(ib - 1 - j) < (unsigned)c.nd[s]) x[s] -= c.LD[adrb + c.dep[s]] * xb;
+      }
+    } else {
+      RR_FOR_S {
+        const int j = c.lane + 32 * s;
+        if ((unsigned)(ia - 1 - j) < (unsigned)c.nd[s]) x[s] -= c.LD[adra + c.dep[s]] * xa;
       }
     }
   }
   RR_FOR_S x[s] *= c.dinv[s];
-  /* forward: x <- L^-1 x, root to leaves */
-#pragma unroll
-  for (int sj = 0; sj < NS; sj++) {
-    const int top = (nv - 32 * sj) < 32 ? (nv - 32 * sj) : 32;
-    for (int src = 0; src < top; src++) {
-      const int j = 32 * sj + src;
-      const int ndj = __shfl_sync(RR_FULL, c.nd[sj], src);
-      if (ndj == 0) continue;
-      const float xj = __shfl_sync(RR_FULL, x[sj], src);
-      const int depj = __shfl_sync(RR_FULL, c.dep[sj], src);
-#pragma unroll
-      for (int s = sj; s < NS; s++) {
+  /* forward: x <- L^-1 x, root to leaves; step dof j updates its descendants i: (unsigned)(i - j - 1) < ndesc[j] */
+#pragma unroll 4
+  for (int st = 0; st < m.nsched_fwd; st++) {
+    const int e = RI(sched_fwd, st), ja = e & 255, jb = (e >> 8) & 255;
+    const float xa = __shfl_sync(RR_FULL, vselect<NS>(x, ja >> 5), ja & 31);
+    const int depa = RI(dof_depth, ja), nda = RI(dof_ndesc, ja);
+    if (jb != 255) {
+      const float xb = __shfl_sync(RR_FULL, vselect<NS>(x, jb >> 5), jb & 31);
+      const int depb = RI(dof_depth, jb), ndb = RI(dof_ndesc, jb);
+      RR_FOR_S {
         const int i = c.lane + 32 * s;
-        if (i > j && i <= j + ndj) x[s] -= c.LD[c.radr[s] + depj] * xj;
+        if ((unsigned)(i - 1 - ja) < (unsigned)nda) x[s] -= c.LD[c.radr[s] + depa] * xa;
+        if ((unsigned)(i - 1 - jb) < (unsigned)ndb) x[s] -= c.LD[c.radr[s] + depb] * xb;
+      }
+    } else {
+      RR_FOR_S {
+        const int i = c.lane + 32 * s;
+        if ((unsigned)(i - 1 - ja) < (unsigned)nda) x[s] -= c.LD[c.radr[s] + depa] * xa;
       }
     }
   }

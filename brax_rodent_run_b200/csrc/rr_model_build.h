@@ -166,6 +166,61 @@ inline void rr_host_model_build(RRHostModel &hm, const int32_t *dir, const int32
   t_M_meta.resize(t_M_colind.size());
   for (size_t e = 0; e < t_M_colind.size(); e++)
     t_M_meta[e] = nv ? (t_M_rowid[e] | (t_M_colind[e] << 8) | (t_dof_rowadr[t_M_colind[e]] << 16)) : 0;
+  /* solve_ld(): two-wide schedules.  backward (leaves -> root): a dof is ready once all its children are done, priority =
+   * number of ancestors (longest remaining path); forward (root -> leaves): ready once its parent is done, priority =
+   * height of the subtree below.  Ready dofs are never ancestor-related, so any two of them are independent. */
+  {
+    std::vector<int> nchild(nv, 0), height(nv, 0);
+    for (int i = nv - 1; i >= 0; i--) {
+      int p = dofparent[i];
+      if (p >= 0) { nchild[p]++; height[p] = std::max(height[p], height[i] + 1); }
+    }
+    auto run = [&](bool backward, std::vector<int32_t> &out) {
+      std::vector<int> pending(nv, 0), done(nv, 0), ready;
+      for (int i = 0; i < nv; i++) {
+        pending[i] = backward ? nchild[i] : (dofparent[i] >= 0 ? 1 : 0);
+        if (pending[i] == 0) ready.push_back(i);
+      }
+      auto prio = [&](int i) { return backward ? t_dof_depth[i] : height[i]; };
+      while (!ready.empty()) {
+        std::sort(ready.begin(), ready.end(), [&](int a, int b) { return prio(a) != prio(b) ? prio(a) > prio(b) : a < b; });
+        std::vector<int> pick;
+        for (size_t q = 0; q < ready.size() && pick.size() < 2; q++) pick.push_back(ready[q]);
+        ready.erase(ready.begin(), ready.begin() + pick.size());
+        /* dofs that do no work in this direction still release their dependants but take no slot */
+        std::vector<int> work;
+        for (int i : pick) {
+          bool has_work = backward ? t_dof_depth[i] > 0 : t_dof_ndesc[i] > 0;
+          if (has_work) work.push_back(i);
+        }
+        if (work.size() == 2) out.push_back(work[0] | (work[1] << 8));
+        else if (work.size() == 1) out.push_back(work[0] | (255 << 8));
+        for (int i : pick) {
+          done[i] = 1;
+          if (backward) {
+            int p = dofparent[i];
+            if (p >= 0 && --pending[p] == 0) ready.push_back(p);
+          } else {
+            for (int k = i + 1; k < nv; k++)
+              if (dofparent[k] == i && --pending[k] == 0) ready.push_back(k);
+          }
+        }
+      }
+    };
+    run(true, t_sched_back);
+    run(false, t_sched_fwd);
+    d.nsched_back = (int)t_sched_back.size();
+    d.nsched_fwd = (int)t_sched_fwd.size();
+    if (t_sched_back.empty()) t_sched_back.push_back(0);
+    if (t_sched_fwd.empty()) t_sched_fwd.push_back(0);
+  }
+  /* factor(): row width rounded up to a power of two (log2), for the lane-group split of short rows */
+  t_dof_log2w.assign(nv, 5);
+  for (int i = 0; i < nv; i++) {
+    int lw = 0;
+    while ((1 << lw) < t_dof_depth[i] + 1 && lw < 5) lw++;
+    t_dof_log2w[i] = lw;
+  }
   {
     int maxdep = 0;
     for (int i = 0; i < nv; i++) maxdep = std::max(maxdep, t_dof_depth[i]);

@@ -102,6 +102,11 @@ static inline unsigned __ballot_sync(unsigned, bool pred) {
 static inline void __syncwarp() { emu::exchange(0, emu::g_lane, 5); }
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 
+struct float2 { float x, y; };
+static inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y; return r; }
+static inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
+static inline int __float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
+
 #define RR_DEV static inline
 #define RR_HOSTDEV static inline
 #define RR_DEV_MEMBER inline
