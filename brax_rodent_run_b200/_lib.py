@@ -33,6 +33,7 @@ _BUF_FIELDS = (
     "obs", "reward", "done", "metrics", "steps", "truncation",
     "first_qpos", "first_qvel", "first_act", "first_qacc_warmstart", "first_time", "first_obs",
     "xpos", "xquat", "subtree_com", "qfrc_actuator", "cinert", "cvel", "contact_dist", "qacc", "solver_niter",
+    "work", "env_order",
 )
 
 
@@ -66,6 +67,7 @@ def load(path: Optional[str] = None):
     L.rr_env_set_task.argtypes = [vp, c_f, ctypes.c_int32, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
                                   ctypes.c_int32]
     L.rr_env_set_wrappers.argtypes = [vp, ctypes.c_int32]
+    L.rr_env_geometry.argtypes = [vp, c_i, c_i, c_i]
     L.rr_env_init.argtypes = [vp, ctypes.POINTER(RRBuffers), vp]
     L.rr_env_step.argtypes = [vp, ctypes.POINTER(RRBuffers), vp, ctypes.c_int32, vp]
     L.rr_env_step_host.argtypes = [vp, ctypes.POINTER(RRBuffers), vp, ctypes.c_int32, vp, vp, vp, vp]
@@ -78,7 +80,7 @@ def load(path: Optional[str] = None):
     L.rr_prof_name.restype = ctypes.c_char_p
     L.rr_launch_count.restype = ctypes.c_longlong
     for name in ("rr_model_create", "rr_model_set_solver", "rr_model_dims", "rr_env_create", "rr_env_set_task",
-                 "rr_env_set_wrappers", "rr_env_init", "rr_env_step", "rr_env_step_host", "rr_gae", "rr_debug_field",
+                 "rr_env_set_wrappers", "rr_env_geometry", "rr_env_init", "rr_env_step", "rr_env_step_host", "rr_gae", "rr_debug_field",
                  "rr_env_set_debug", "rr_env_set_profile"):
         getattr(L, name).restype = ctypes.c_int
     _libs[path] = L

@@ -9,6 +9,7 @@
  */
 #include <cuda_runtime.h>
 #include <cstdio>
+#include <cstdlib>
 #include <math_constants.h>
 
 /* production kernels: debug-dump / clock64 hooks compiled out */
@@ -51,7 +52,9 @@ __global__ void __launch_bounds__(32 * RR_MAX_WPB, 1) rr_step_kernel(const __gri
    * locality); passes beyond the batch are padding: they recompute the last environment and store nothing */
   const int stride = gridDim.x * wpb, trips = (a.B + stride - 1) / stride;
   for (int it = 0; it < trips; it++) {
-    const int env = it * stride + blockIdx.x * wpb + warp;
+    const int slot = it * stride + blockIdx.x * wpb + warp;
+    int env = slot;
+    if (a.env_order) { env = a.env_order[slot]; if (env < 0) env = a.B; } /* idle slot -> padding pass */
     if (DBG) rr_dbg::env_run<NS>(m, a, env, blockIdx.x * wpb + warp, sm, ti, tf, lane);
     else rr::env_run<NS>(m, a, env, blockIdx.x * wpb + warp, sm, ti, tf, lane);
     __syncwarp();
@@ -103,8 +106,7 @@ static int rrb_num_slots() {
 }
 static int rrb_sync(void *stream) { return rrb_check(cudaStreamSynchronize((cudaStream_t)stream), "cudaStreamSynchronize"); }
 
-template <int NS, bool DBG>
-static int rrb_launch_ns(const RRModelDev &m, const RRStepArgs &a, void *stream) {
+static int rrb_geometry(const RRModelDev &m, int B, int *ctas, int *wpb_out) {
   const size_t tables = ((size_t)m.ni + m.nf) * 4, per_env = (size_t)m.sm.total * sizeof(float);
   if (tables + per_env > RR_SMEM_MAX) {
     snprintf(g_cuda_err, sizeof(g_cuda_err), "model needs %zu B of shared memory per environment (+%zu B tables) > %d", per_env,
@@ -113,23 +115,36 @@ static int rrb_launch_ns(const RRModelDev &m, const RRStepArgs &a, void *stream)
   }
   int wpb = (int)((RR_SMEM_MAX - tables) / per_env);
   if (wpb > RR_MAX_WPB) wpb = RR_MAX_WPB;
-  size_t smem = tables + per_env * wpb;
-  /* per-device one-time setup (SM count, opt-in shared memory) */
-  static int n_sm_dev[64] = {0};
+  if (const char *ov = getenv("RR_WPB")) { /* developer knob: fewer environments per CTA (occupancy experiments) */
+    int v = atoi(ov);
+    if (v >= 1 && v < wpb) wpb = v;
+  }
+  int dev = 0, n_sm = 0;
+  if (rrb_check(cudaGetDevice(&dev), "cudaGetDevice") ||
+      rrb_check(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev), "cudaDeviceGetAttribute"))
+    return 1;
+  int grid = (B + wpb - 1) / wpb;
+  if (grid > n_sm) grid = n_sm;
+  *ctas = grid;
+  *wpb_out = wpb;
+  return 0;
+}
+
+template <int NS, bool DBG>
+static int rrb_launch_ns(const RRModelDev &m, const RRStepArgs &a, void *stream) {
+  int grid = 1, wpb = 1;
+  if (rrb_geometry(m, a.B, &grid, &wpb)) return 1;
+  const size_t smem = ((size_t)m.ni + m.nf) * 4 + (size_t)m.sm.total * sizeof(float) * wpb;
+  static bool configured[64] = {false};
   int dev = 0;
-  if (rrb_check(cudaGetDevice(&dev), "cudaGetDevice")) return 1;
+  cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64) dev = 0;
-  if (n_sm_dev[dev] == 0) {
-    int n = 0;
-    if (rrb_check(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev), "cudaDeviceGetAttribute") ||
-        rrb_check(cudaFuncSetAttribute(rr_step_kernel<NS, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, RR_SMEM_MAX),
+  if (!configured[dev]) {
+    if (rrb_check(cudaFuncSetAttribute(rr_step_kernel<NS, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, RR_SMEM_MAX),
                   "cudaFuncSetAttribute(smem)"))
       return 1;
-    n_sm_dev[dev] = n;
+    configured[dev] = true;
   }
-  const int n_sm = n_sm_dev[dev];
-  int grid = (a.B + wpb - 1) / wpb;
-  if (grid > n_sm) grid = n_sm;
   rr_step_kernel<NS, DBG><<<grid, 32 * wpb, smem, (cudaStream_t)stream>>>(m, a);
   return rrb_check(cudaGetLastError(), "rr_step_kernel launch");
 }

@@ -7,6 +7,7 @@
  *   int  rrb_h2d(void *dst, const void *src, size_t bytes, void *stream);
  *   int  rrb_d2h(void *dst, const void *src, size_t bytes, void *stream);
  *   int  rrb_sync(void *stream);
+ *   int  rrb_geometry(const RRModelDev &m, int B, int *ctas, int *wpb);
  *   int  rrb_num_slots();                      (upper bound on concurrently resident warps = scratch slots)
  *   int  rrb_launch_step(const RRModelDev &m, const RRStepArgs &a, void *stream);
  *   int  rrb_launch_gae(...);
@@ -123,7 +124,7 @@ extern "C" int rr_debug_field(const rr_model *m, const char *name, int32_t *offs
   return rr_fail(RR_EINVAL, std::string("rr_debug_field: unknown field ") + name);
 }
 
-static const char *const kProfNames[RR_NPROF] = {"load", "kinematics", "com_pos", "crb", "mass_matrix", "factor", "com_vel",
+static const char *const kProfNames[RR_NPROF] = {"load", "kinematics", "com_pos", "solver_cost_JTf", "mass_matrix", "factor", "solver_Minv_grad",
                                                   "rne", "smooth", "collision", "make_constraint", "solver_init",
                                                   "solver_linesearch", "solver_update", "euler", "epilogue"};
 extern "C" int rr_prof_count(void) { return RR_NPROF; }
@@ -155,7 +156,7 @@ extern "C" int rr_env_create(const rr_model *cm, int32_t num_envs, int32_t devic
     delete e;
     return rr_fail(RR_ECUDA, rrb_error());
   }
-  e->scratch_stride = ((m->dev.nJ + 3) & ~3) + 5 * ((m->dev.nefc + 3) & ~3) + 4;
+  e->scratch_stride = 5 * ((m->dev.nefc + 3) & ~3) + 4;
   if (rrb_malloc((void **)&e->d_scratch, (size_t)rrb_num_slots() * e->scratch_stride * sizeof(float))) {
     rrb_free(e->d_action_stage);
     delete e;
@@ -195,6 +196,16 @@ extern "C" int rr_env_set_task(rr_env *e, const float *track_pos, int32_t track_
 extern "C" int rr_env_set_wrappers(rr_env *e, int32_t episode_length) {
   if (!e || episode_length < 0) return rr_fail(RR_EINVAL, "rr_env_set_wrappers: bad argument");
   e->episode_length = episode_length;
+  return RR_OK;
+}
+
+extern "C" int rr_env_geometry(const rr_env *e, int32_t *ctas, int32_t *envs_per_cta, int32_t *passes) {
+  if (!e) return rr_fail(RR_EINVAL, "rr_env_geometry: null env");
+  int g = 1, w = 1;
+  if (rrb_set_device(e->device) || rrb_geometry(e->model->dev, e->B, &g, &w)) return rr_fail(RR_ECUDA, rrb_error());
+  if (ctas) *ctas = g;
+  if (envs_per_cta) *envs_per_cta = w;
+  if (passes) *passes = (e->B + g * w - 1) / (g * w);
   return RR_OK;
 }
 
@@ -239,6 +250,7 @@ static int rr_fill_args(rr_env *e, const rr_buffers *b, const float *action, int
   a.first_warm = b->first_qacc_warmstart; a.first_time = b->first_time; a.first_obs = b->first_obs;
   a.xpos = b->xpos; a.xquat = b->xquat; a.subtree_com = b->subtree_com; a.qfrc_actuator = b->qfrc_actuator;
   a.cinert = b->cinert; a.cvel = b->cvel; a.contact_dist = b->contact_dist; a.qacc = b->qacc; a.niter = b->solver_niter;
+  a.work = b->work; a.env_order = b->env_order;
   a.dbg.buf = e->d_dbg;
   a.dbg.stride = rr_debug_stride_of(e->model->dev);
   a.prof = e->d_prof;

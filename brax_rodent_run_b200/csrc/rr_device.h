@@ -16,10 +16,10 @@
 #define RR_DEV_INT_TABLES(X)                                                                              \
   X(body_parentid) X(body_rootslot) X(body_jntadr) X(body_jntnum) X(level_adr) X(level_body)              \
   X(jnt_type) X(jnt_qposadr) X(jnt_dofadr) X(jnt_bodyid)                                                  \
-  X(dof_bodyid) X(dof_depth) X(dof_ndesc) X(dof_rowadr) X(dof_log2w) X(M_meta) X(sched_back) X(sched_fwd)                            \
+  X(dof_bodyid) X(dof_depth) X(dof_ndesc) X(dof_rowadr) X(dof_log2w) X(dof_pack) X(M_meta) X(sched_back) X(sched_fwd)                            \
   X(act_dofadr) X(act_qposadr) X(act_dyntype) X(act_gaintype) X(act_biastype) X(act_ctrllimited)          \
   X(act_forcelimited) X(act_actadr)                                                                       \
-  X(pair_fn) X(pair_body) X(pair_conadr) X(pair_lastdof) X(con_pair) X(con_Jadr)                          \
+  X(pair_fn) X(pair_body) X(pair_conadr) X(pair_lastdof) X(pair_cb) X(cb_lastdof) X(cb_conadr) X(cb_conlist) X(con_pair)                          \
   X(limit_qposadr) X(limit_dofadr)
 
 #define RR_DEV_FLOAT_TABLES(X)                                                                            \
@@ -35,22 +35,22 @@
  *   A persistent state; B mass matrix + factor; C a union recycled by phase:
  *     C1 kinematics .. smooth forces : xpos xquat cinert cdof | qfrc_act cvel cacc cfrc  (crb fcrb overlay cvel..cfrc)
  *     C2 collision .. solver         : xpos xquat cdof stay (collision / Jacobians read them); the contact arrays,
- *                                      Jacobian blocks (capJ floats) and constraint rows (capR rows) overlay
+ *                                      per-contact six-vectors and constraint rows (capR rows) overlay
  *                                      cinert / qfrc_act / cvel / cacc / cfrc, which are dead by then (their
  *                                      observation slices are written to HBM before the solver in the last substep).
  */
 struct RRSmem {
-  int qpos, qvel, act, ctrl, actdot, com, vbuf, Dinv, xq1; /* A */
+  int qpos, qvel, act, ctrl, actdot, com, vbuf, Dinv, xq1, prof_acc; /* A */
   int M, LD;                                               /* B */
   int xpos, xquat, cdof;                                   /* C, live through the Jacobian build */
   int cinert, qfrc_act, cvel, cacc, cfrc, crb, fcrb;       /* C1 */
-  int con_dist, con_pos, con_frame, cact, cmeta, con_J, row_D; /* C2 (rows: D aref Jaref jv id, capR each, from row_D) */
-  int capJ, capR;
+  int con_dist, cab, cscr, cbv, cact, ckidx, row_D; /* C2: cab = 18 floats per contact; rows: D aref Jaref jv id, capR each */
+  int capR;
   int total; /* floats per environment */
 };
 
 struct RRModelDev {
-  int nq, nv, nu, na, nbody, njnt, ngeom, nM, npair, ncon, nlimit, nefc, nlevel, nroot, nJ;
+  int nq, nv, nu, na, nbody, njnt, ngeom, nM, npair, ncon, nlimit, nefc, nlevel, nroot, ncb;
   int solver, iterations, ls_iterations;
   int nsched_back, nsched_fwd; /* steps of the two-wide triangular-solve schedules */
   float timestep, gravity[3], tolerance, ls_tolerance, impratio, meaninertia;
@@ -99,9 +99,11 @@ struct RRStepArgs {
   /* optional extra outputs of the last forward pass (null = skip) */
   float *xpos, *xquat, *subtree_com, *qfrc_actuator, *cinert, *cvel, *contact_dist, *qacc;
   int *niter; /* [B] solver iterations executed in the last substep */
+  float *work;          /* [B] clock cycles spent on this environment (load-balancing hint) or null */
+  const int *env_order; /* [slots] slot -> env (-1 idle) or null */
   RRDebug dbg;
   float *scratch;     /* [warp slots, scratch_stride] global overflow for contact Jacobians / constraint rows */
-  int scratch_stride; /* floats: align4(nJ) + 5 nefc */
+  int scratch_stride; /* floats: 5 align4(nefc) */
   long long *prof; /* [B, RR_NPROF] clock64 deltas or null */
 };
 

@@ -54,7 +54,15 @@
 #ifndef RR_SYNC_LEVEL
 #define RR_SYNC_LEVEL 2 /* 1: per substep; 2: + before each factorisation and the collision phase; 3: + per CG iteration */
 #endif
-#define RR_CTA_SYNC_AT(level) do { if (RR_SYNC_LEVEL >= (level)) RR_CTA_SYNC(); } while (0)
+/* the time spent waiting at the rendezvous is excluded from the per-environment work estimate (c.wait) */
+#define RR_CTA_SYNC_AT(level)                                 \
+  do {                                                        \
+    if (RR_SYNC_LEVEL >= (level)) {                           \
+      const long long t_sync_ = c.a.work ? RR_CLOCK() : 0;    \
+      RR_CTA_SYNC();                                          \
+      if (c.a.work) c.wait += RR_CLOCK() - t_sync_;           \
+    }                                                         \
+  } while (0)
 
 #define RR_FULL 0xffffffffu
 #define RR_MINVAL 1e-15f
@@ -173,10 +181,11 @@ struct Ctx {
   const int32_t *ti; /* shared-memory copies of the model tables */
   const float *tf;
   float *qpos, *qvel, *act, *ctrl, *actdot, *xpos, *xquat, *com, *cinert, *cdof, *cvel, *M, *LD, *Dinv, *vbuf, *qfrc_act;
-  float *crb, *fcrb, *cacc, *cfrc, *con_dist, *con_pos, *con_frame, *con_J, *row_D, *row_aref, *row_Jaref, *row_jv;
-  int *row_id, *cact, *cmeta;
+  float *crb, *fcrb, *cacc, *cfrc, *con_dist, *cab, *cscr, *cbv, *row_D, *row_aref, *row_Jaref, *row_jv;
+  int *row_id, *cact, *ckidx;
+  float *prof_acc; /* RR_NPROF per-stage cycle sums (debug builds) */
   float *xq1; /* xquat of body 1 saved for the observation (xquat itself is recycled by the solver phase) */
-  float *sm_base, *gJ, *grows; /* shared-memory base; global overflow for contact Jacobians / rows */
+  float *sm_base, *grows; /* shared-memory base; global overflow for constraint rows */
   /* per-lane dof metadata: dof i = lane + 32 s */
   int radr[NS], dep[NS], nd[NS];
   float dinv[NS];
@@ -186,6 +195,7 @@ struct Ctx {
   bool live;         /* false: padding pass of a persistent warp (keeps CTA barriers matched); no global stores */
   bool last_substep; /* the forward pass whose cinert / cvel / qfrc_actuator the observation reports */
   int niter;
+  long long wait; /* cycles spent at CTA rendezvous */
   float *dbg;
   long long tprev;
 
@@ -203,16 +213,16 @@ struct Ctx {
       : m(m_), a(a_), env(env_), lane(lane_), ti(ti_), tf(tf_) {
     const RRSmem &s = m.sm;
     sm_base = sm;
-    gJ = a.scratch + (size_t)slot_ * a.scratch_stride;
-    grows = gJ + ((m.nJ + 3) & ~3);
-    cmeta = (int *)(sm + s.cmeta);
+    grows = a.scratch + (size_t)slot_ * a.scratch_stride;
     xq1 = sm + s.xq1;
+    prof_acc = sm + s.prof_acc;
     qpos = sm + s.qpos; qvel = sm + s.qvel; act = sm + s.act; ctrl = sm + s.ctrl; actdot = sm + s.actdot;
     xpos = sm + s.xpos; xquat = sm + s.xquat; com = sm + s.com; cinert = sm + s.cinert; cdof = sm + s.cdof;
     cvel = sm + s.cvel; M = sm + s.M; LD = sm + s.LD; Dinv = sm + s.Dinv; vbuf = sm + s.vbuf; qfrc_act = sm + s.qfrc_act;
     crb = sm + s.crb; fcrb = sm + s.fcrb; cacc = sm + s.cacc; cfrc = sm + s.cfrc;
-    con_dist = sm + s.con_dist; con_pos = sm + s.con_pos; con_frame = sm + s.con_frame; con_J = sm + s.con_J;
+    con_dist = sm + s.con_dist; cab = sm + s.cab; cscr = sm + s.cscr; cbv = sm + s.cbv;
     cact = (int *)(sm + s.cact);
+    ckidx = (int *)(sm + s.ckidx);
     use_rows(true);
 #pragma unroll
     for (int s_ = 0; s_ < NS; s_++) {
@@ -227,6 +237,7 @@ struct Ctx {
     niter = 0;
     last_substep = false;
     live = true;
+    wait = 0;
     dbg = a.dbg.buf ? a.dbg.buf + (size_t)env * a.dbg.stride : nullptr;
     tprev = 0;
   }
@@ -234,15 +245,21 @@ struct Ctx {
 
 #define RR_FOR_S _Pragma("unroll") for (int s = 0; s < NS; s++)
 
+/* per-stage cycle counters accumulate in shared memory (a global read-modify-write per call would dominate the short
+ * stages) and are flushed once per environment by prof_flush */
 template <int NS>
 RR_DEV void prof(Ctx<NS> &c, int id) {
   if (RR_WITH_DEBUG && c.a.prof && c.live) {
     long long t = RR_CLOCK();
-    if (c.lane == 0) c.a.prof[(size_t)c.env * RR_NPROF + id] += t - c.tprev;
-    c.tprev = t;
+    if (c.lane == 0) c.prof_acc[id] += (float)(t - c.tprev);
+    c.tprev = RR_CLOCK();
   }
 }
-
+template <int NS>
+RR_DEV void prof_flush(Ctx<NS> &c) {
+  if (RR_WITH_DEBUG && c.a.prof && c.live && c.lane == 0)
+    for (int i = 0; i < RR_NPROF; i++) c.a.prof[(size_t)c.env * RR_NPROF + i] += (long long)c.prof_acc[i];
+}
 template <int NS>
 RR_DEV float vdot(const float (&x)[NS], const float (&y)[NS]) {
   float t = 0.f;
@@ -574,25 +591,23 @@ RR_DEV void factor(Ctx<NS> &c, float diag_scale) {
 template <int NS>
 RR_DEV void solve_ld(Ctx<NS> &c, float (&x)[NS]) {
   const RRModelDev &m = c.m;
+  /* Straight-line loop bodies (no branch on the optional second entry; 255 = none is folded into the predicate) so that
+   * the unrolled schedule / metadata / coefficient loads of later steps can be hoisted above the dependent
+   * shuffle -> FMA chain. */
   /* backward: x <- L^-T x, leaves to root; step dof i updates its ancestors j: (unsigned)(i - j - 1) < ndesc[j] */
 #pragma unroll 4
   for (int st = 0; st < m.nsched_back; st++) {
     const int e = RI(sched_back, st), ia = e & 255, ib = (e >> 8) & 255;
+    const bool hb = ib != 255;
+    const int adra = RI(dof_rowadr, ia), adrb = RI(dof_rowadr, hb ? ib : 0);
     const float xa = __shfl_sync(RR_FULL, vselect<NS>(x, ia >> 5), ia & 31);
-    const int adra = RI(dof_rowadr, ia);
-    if (ib != 255) {
-      const float xb = __shfl_sync(RR_FULL, vselect<NS>(x, ib >> 5), ib & 31);
-      const int adrb = RI(dof_rowadr, ib);
-      RR_FOR_S {
-        const int j = c.lane + 32 * s;
-        if ((unsigned)(ia - 1 - j) < (unsigned)c.nd[s]) x[s] -= c.LD[adra + c.dep[s]] * xa;
-        if ((unsigned)(ib - 1 - j) < (unsigned)c.nd[s]) x[s] -= c.LD[adrb + c.dep[s]] * xb;
-      }
-    } else {
-      RR_FOR_S {
-        const int j = c.lane + 32 * s;
-        if ((unsigned)(ia - 1 - j) < (unsigned)c.nd[s]) x[s] -= c.LD[adra + c.dep[s]] * xa;
-      }
+    const float xb = __shfl_sync(RR_FULL, vselect<NS>(x, ib >> 5), ib & 31);
+    RR_FOR_S {
+      const int j = c.lane + 32 * s;
+      const float la = ((unsigned)(ia - 1 - j) < (unsigned)c.nd[s]) ? c.LD[adra + c.dep[s]] : 0.f;
+      const float lb = (hb && (unsigned)(ib - 1 - j) < (unsigned)c.nd[s]) ? c.LD[adrb + c.dep[s]] : 0.f;
+      x[s] -= la * xa;
+      x[s] -= lb * xb;
     }
   }
   RR_FOR_S x[s] *= c.dinv[s];
@@ -600,21 +615,16 @@ RR_DEV void solve_ld(Ctx<NS> &c, float (&x)[NS]) {
 #pragma unroll 4
   for (int st = 0; st < m.nsched_fwd; st++) {
     const int e = RI(sched_fwd, st), ja = e & 255, jb = (e >> 8) & 255;
+    const bool hb = jb != 255;
+    const int pa = RI(dof_pack, ja), pb = hb ? RI(dof_pack, jb) : 0; /* rowadr | depth << 16 | ndesc << 24 */
     const float xa = __shfl_sync(RR_FULL, vselect<NS>(x, ja >> 5), ja & 31);
-    const int depa = RI(dof_depth, ja), nda = RI(dof_ndesc, ja);
-    if (jb != 255) {
-      const float xb = __shfl_sync(RR_FULL, vselect<NS>(x, jb >> 5), jb & 31);
-      const int depb = RI(dof_depth, jb), ndb = RI(dof_ndesc, jb);
-      RR_FOR_S {
-        const int i = c.lane + 32 * s;
-        if ((unsigned)(i - 1 - ja) < (unsigned)nda) x[s] -= c.LD[c.radr[s] + depa] * xa;
-        if ((unsigned)(i - 1 - jb) < (unsigned)ndb) x[s] -= c.LD[c.radr[s] + depb] * xb;
-      }
-    } else {
-      RR_FOR_S {
-        const int i = c.lane + 32 * s;
-        if ((unsigned)(i - 1 - ja) < (unsigned)nda) x[s] -= c.LD[c.radr[s] + depa] * xa;
-      }
+    const float xb = __shfl_sync(RR_FULL, vselect<NS>(x, jb >> 5), jb & 31);
+    RR_FOR_S {
+      const int i = c.lane + 32 * s;
+      const float la = ((unsigned)(i - 1 - ja) < ((unsigned)pa >> 24)) ? c.LD[c.radr[s] + ((pa >> 16) & 255)] : 0.f;
+      const float lb = ((unsigned)(i - 1 - jb) < ((unsigned)pb >> 24)) ? c.LD[c.radr[s] + ((pb >> 16) & 255)] : 0.f;
+      x[s] -= la * xa;
+      x[s] -= lb * xb;
     }
   }
 }
@@ -821,8 +831,8 @@ RR_DEV void collision(Ctx<NS> &c) {
       float dist = dot3(d, n) - size[0];
       c.con_dist[ca] = dist;
 #pragma unroll
-      for (int k = 0; k < 3; k++) c.con_pos[3 * ca + k] = gp[k] - n[k] * (size[0] + 0.5f * dist);
-      make_frame(c.con_frame + 9 * ca, n);
+      for (int k = 0; k < 3; k++) c.cab[18 * ca + 9 + k] = gp[k] - n[k] * (size[0] + 0.5f * dist);
+      make_frame(c.cab + 18 * ca, n);
     } else {
       float q[4], gm[9];
       quat_mul(q, xq, gq);
@@ -848,9 +858,9 @@ RR_DEV void collision(Ctx<NS> &c) {
           float dist = dot3(d, n) - size[0];
           c.con_dist[ca + e] = dist;
 #pragma unroll
-          for (int k = 0; k < 3; k++) c.con_pos[3 * (ca + e) + k] = cp[k] - n[k] * (size[0] + 0.5f * dist);
+          for (int k = 0; k < 3; k++) c.cab[18 * (ca + e) + 9 + k] = cp[k] - n[k] * (size[0] + 0.5f * dist);
 #pragma unroll
-          for (int k = 0; k < 9; k++) c.con_frame[9 * (ca + e) + k] = frame[k];
+          for (int k = 0; k < 9; k++) c.cab[18 * (ca + e) + k] = frame[k];
         }
       } else { /* plane - ellipsoid */
         float nl[3], sv[3], lp[3], wp[3];
@@ -867,26 +877,27 @@ RR_DEV void collision(Ctx<NS> &c) {
         float dist = dot3(d, n);
         c.con_dist[ca] = dist;
 #pragma unroll
-        for (int k = 0; k < 3; k++) c.con_pos[3 * ca + k] = wp[k] - n[k] * dist * 0.5f;
-        make_frame(c.con_frame + 9 * ca, n);
+        for (int k = 0; k < 3; k++) c.cab[18 * ca + 9 + k] = wp[k] - n[k] * dist * 0.5f;
+        make_frame(c.cab + 18 * ca, n);
       }
     }
   }
   __syncwarp();
   dbg_copy<NS>(c, RR_DBG_CON_DIST, c.con_dist, m.ncon);
-  dbg_copy<NS>(c, RR_DBG_CON_POS, c.con_pos, 3 * m.ncon);
-  dbg_copy<NS>(c, RR_DBG_CON_FRAME, c.con_frame, 9 * m.ncon);
+  if (RR_WITH_DEBUG && c.dbg) {
+    float *dP = c.dbg + dbg_offset(m, RR_DBG_CON_POS), *dF = c.dbg + dbg_offset(m, RR_DBG_CON_FRAME);
+    for (int i = c.lane; i < 3 * m.ncon; i += 32) dP[i] = c.cab[18 * (i / 3) + 9 + i % 3];
+    for (int i = c.lane; i < 9 * m.ncon; i += 32) dF[i] = c.cab[18 * (i / 9) + i % 9];
+  }
 }
 
 /* ------------------------------------------------------------------------------------------ constraint rows (B.5) */
-/* Active contact k (compact index) carries: cact[k] = contact id, cmeta[4k..4k+3] = {Jadr, chain length, rowadr of the
- * chain's last dof, last dof}.  Its Jacobian block is 3 x len floats at Jbase(k): shared memory while the running
- * offset fits capJ, else the per-warp global scratch (rare: e.g. every paw and tail capsule touching at once). */
-template <int NS>
-RR_DEV const float *jblock(const Ctx<NS> &c, int k) {
-  int jadr = c.cmeta[4 * k], len = c.cmeta[4 * k + 1];
-  return (jadr + 3 * len <= c.m.sm.capJ) ? c.con_J + jadr : c.gJ + jadr;
-}
+/* Contact Jacobians are never materialised.  A contact row in frame direction r is
+ *   J_r[d] = fr_r . (cdof_lin[d] + cdof_ang[d] x off) = [off x fr_r ; fr_r] . cdof[d]        (off = contact point - tree COM)
+ * so each contact keeps 3 six-vectors cab[c][r] = [off x fr_r ; fr_r] (18 floats, always in shared memory), and
+ *   J v   = cab . V_b,   V_b = sum over the chain of body b of cdof[d] v[d]     (spatial velocity induced by v)
+ *   J' f  : F_b = sum over contacts on b of g_r cab[c][r],  qfc[d] = cdof[d] . F_b for d in chain(b)
+ * with one V_b / F_b per contact BODY (10 for the rodent's 34 contacts): work no longer scales with chain x contacts. */
 
 /* rows: out[r] = J_r . v for the compact active rows; v staged in vbuf by the caller (already synced). */
 template <int NS>
@@ -897,23 +908,32 @@ RR_DEV void mul_j(Ctx<NS> &c, float *out) {
     float sg = (id & RR_SIGN_BIT) ? -1.f : 1.f;
     out[r] = sg * c.vbuf[RI(limit_dofadr, id & 0xffff)];
   }
-  /* contacts: the 3 frame-row dot products per contact go to a3 (con_pos is dead once the Jacobians exist) */
-  float *a3 = c.con_pos;
+  /* V_b for every contact body: item = (body slot, component) */
+  for (int it = c.lane; it < 6 * m.ncb; it += 32) {
+    int kb = it / 6, q = it - 6 * kb;
+    int ld = RI(cb_lastdof, kb);
+    int len = RI(dof_depth, ld) + 1, adr = RI(dof_rowadr, ld);
+    float acc = 0.f;
+#pragma unroll 4
+    for (int t = 0; t < len; t++) {
+      int d = RR_META_COL(RI(M_meta, adr + t));
+      acc += c.cdof[6 * d + q] * c.vbuf[d];
+    }
+    c.cbv[it] = acc;
+  }
+  __syncwarp();
   for (int it = c.lane; it < 3 * c.nca; it += 32) {
     int k = it / 3, r3 = it - 3 * k;
-    int len = c.cmeta[4 * k + 1], adr = c.cmeta[4 * k + 2];
-    const float *J = jblock<NS>(c, k) + r3 * len;
-    float acc = 0.f;
-#pragma unroll 2
-    for (int t = 0; t < len; t++) acc += J[t] * c.vbuf[RR_META_COL(RI(M_meta, adr + t))];
-    a3[it] = acc;
+    int cc = c.cact[k];
+    const float *ab = c.cab + 18 * cc + 6 * r3, *V = c.cbv + 6 * RI(pair_cb, RI(con_pair, cc));
+    c.cscr[it] = ab[0] * V[0] + ab[1] * V[1] + ab[2] * V[2] + ab[3] * V[3] + ab[4] * V[4] + ab[5] * V[5];
   }
   __syncwarp();
   for (int r = c.lane; r < 4 * c.nca; r += 32) {
     int k = r >> 2, q = r & 3;
     float mu = RF(pair_mu, RI(con_pair, c.cact[k]));
     float f = (q & 1) ? -mu : mu;
-    out[c.nla + r] = a3[3 * k] + a3[3 * k + 1 + (q >> 1)] * f;
+    out[c.nla + r] = c.cscr[3 * k] + c.cscr[3 * k + 1 + (q >> 1)] * f;
   }
   __syncwarp();
 }
@@ -922,7 +942,6 @@ RR_DEV void mul_j(Ctx<NS> &c, float *out) {
 template <int NS>
 RR_DEV void mul_jt(Ctx<NS> &c, const float *frc, float (&qfc)[NS]) {
   const RRModelDev &m = c.m;
-  float *g3 = c.con_pos;
   __syncwarp();
   for (int i = c.lane; i < m.nv; i += 32) c.vbuf[i] = 0.f;
   __syncwarp();
@@ -934,9 +953,27 @@ RR_DEV void mul_jt(Ctx<NS> &c, const float *frc, float (&qfc)[NS]) {
   for (int k = c.lane; k < c.nca; k += 32) {
     const float *f = frc + c.nla + 4 * k;
     float mu = RF(pair_mu, RI(con_pair, c.cact[k]));
-    g3[3 * k] = f[0] + f[1] + f[2] + f[3];
-    g3[3 * k + 1] = mu * f[0] - mu * f[1];
-    g3[3 * k + 2] = mu * f[2] - mu * f[3];
+    c.cscr[3 * k] = f[0] + f[1] + f[2] + f[3];
+    c.cscr[3 * k + 1] = mu * f[0] - mu * f[1];
+    c.cscr[3 * k + 2] = mu * f[2] - mu * f[3];
+  }
+  __syncwarp();
+  /* F_b: item = (body slot, component), summed over that body's (static) contact list; ckidx maps a contact to its
+   * compact active index (-1 = inactive) */
+  for (int it = c.lane; it < 6 * m.ncb; it += 32) {
+    int kb = it / 6, q = it - 6 * kb;
+    float acc = 0.f;
+    const int beg = RI(cb_conadr, kb), end = RI(cb_conadr, kb + 1);
+#pragma unroll 2
+    for (int e = beg; e < end; e++) {
+      int cc = RI(cb_conlist, e);
+      int k = c.ckidx[cc];
+      if (k >= 0) {
+        const float *ab = c.cab + 18 * cc + q;
+        acc += c.cscr[3 * k] * ab[0] + c.cscr[3 * k + 1] * ab[6] + c.cscr[3 * k + 2] * ab[12];
+      }
+    }
+    c.cbv[it] = acc;
   }
   __syncwarp();
   RR_FOR_S {
@@ -944,12 +981,13 @@ RR_DEV void mul_jt(Ctx<NS> &c, const float *frc, float (&qfc)[NS]) {
     float acc = 0.f;
     if (i < m.nv) {
       acc = c.vbuf[i];
-      for (int k = 0; k < c.nca; k++) {
-        int ld = c.cmeta[4 * k + 3];
-        if (i <= ld && ld <= i + c.nd[s]) {
-          int len = c.cmeta[4 * k + 1];
-          const float *J = jblock<NS>(c, k) + c.dep[s];
-          acc += J[0] * g3[3 * k] + J[len] * g3[3 * k + 1] + J[2 * len] * g3[3 * k + 2];
+      const float *cd = c.cdof + 6 * i;
+#pragma unroll 2
+      for (int kb = 0; kb < m.ncb; kb++) {
+        int ld = RI(cb_lastdof, kb);
+        if ((unsigned)(ld - i) <= (unsigned)c.nd[s]) {
+          const float *F = c.cbv + 6 * kb;
+          acc += cd[0] * F[0] + cd[1] * F[1] + cd[2] * F[2] + cd[3] * F[3] + cd[4] * F[4] + cd[5] * F[5];
         }
       }
     }
@@ -979,7 +1017,11 @@ RR_DEV void make_constraint(Ctx<NS> &c) {
     bool active = false;
     if (cc < m.ncon) active = (c.con_dist[cc] - RF(pair_margin, RI(con_pair, cc))) < 0.f;
     unsigned mask = __ballot_sync(RR_FULL, active);
-    if (active) c.cact[nca + __popc(mask & lt)] = cc;
+    if (cc < m.ncon) {
+      int k = nca + __popc(mask & lt);
+      if (active) c.cact[k] = cc;
+      c.ckidx[cc] = active ? k : -1;
+    }
     nca += __popc(mask);
   }
   const int nra = nla + 4 * nca;
@@ -1015,52 +1057,36 @@ RR_DEV void make_constraint(Ctx<NS> &c) {
     }
     r0 += __popc(mask);
   }
-  /* contact metadata: running Jacobian offsets (serial prefix over <= ncon active contacts, done by every lane) */
-  {
-    int jadr = 0;
-    for (int k = 0; k < nca; k++) {
-      int p = RI(con_pair, c.cact[k]);
-      int ld = RI(pair_lastdof, p);
-      int len = RI(dof_depth, ld) + 1;
-      if (c.lane == 0) { c.cmeta[4 * k] = jadr; c.cmeta[4 * k + 1] = len; c.cmeta[4 * k + 2] = RI(dof_rowadr, ld); c.cmeta[4 * k + 3] = ld; }
-      jadr += 3 * len;
-    }
-  }
-  __syncwarp();
-  /* contact Jacobian blocks (3 x chain) and row parameters */
-  for (int k = 0; k < nca; k++) {
+  /* active contacts: (frame, pos) -> cab = [off x fr_r ; fr_r], r = 0..2, in place; row parameters */
+  for (int k = c.lane; k < nca; k += 32) {
     int cc = c.cact[k];
     int p = RI(con_pair, cc);
-    int len = c.cmeta[4 * k + 1], adr = c.cmeta[4 * k + 2];
     int rs = RI(body_rootslot, RI(pair_body, p));
-    float off[3], fr[9];
+    float *ab = c.cab + 18 * cc;
+    float fr[9], off[3];
 #pragma unroll
-    for (int q = 0; q < 3; q++) off[q] = c.con_pos[3 * cc + q] - c.com[3 * rs + q];
+    for (int q = 0; q < 9; q++) fr[q] = ab[q];
 #pragma unroll
-    for (int q = 0; q < 9; q++) fr[q] = c.con_frame[9 * cc + q];
-    float *J = const_cast<float *>(jblock<NS>(c, k));
-    for (int t = c.lane; t < len; t += 32) {
-      int d = RR_META_COL(RI(M_meta, adr + t));
-      float cd[6], cr[3], jp[3];
+    for (int q = 0; q < 3; q++) off[q] = ab[9 + q] - c.com[3 * rs + q];
 #pragma unroll
-      for (int q = 0; q < 6; q++) cd[q] = c.cdof[6 * d + q];
-      cross3(cr, cd, off);
+    for (int r3 = 0; r3 < 3; r3++) {
+      float x[3];
+      cross3(x, off, fr + 3 * r3);
 #pragma unroll
-      for (int q = 0; q < 3; q++) jp[q] = cd[3 + q] + cr[q];
-#pragma unroll
-      for (int r3 = 0; r3 < 3; r3++) J[r3 * len + t] = fr[3 * r3] * jp[0] + fr[3 * r3 + 1] * jp[1] + fr[3 * r3 + 2] * jp[2];
+      for (int q = 0; q < 3; q++) { ab[6 * r3 + q] = x[q]; ab[6 * r3 + 3 + q] = fr[3 * r3 + q]; }
     }
-    if (c.lane < 4) {
-      float pos = c.con_dist[cc] - RF(pair_margin, p);
-      float sr[2] = {RF(pair_solref, 2 * p), RF(pair_solref, 2 * p + 1)}, si[5], kk, b, imp;
+    float pos = c.con_dist[cc] - RF(pair_margin, p);
+    float sr[2] = {RF(pair_solref, 2 * p), RF(pair_solref, 2 * p + 1)}, si[5], kk, b, imp;
 #pragma unroll
-      for (int q = 0; q < 5; q++) si[q] = RF(pair_solimp, 5 * p + q);
-      kbi(m.timestep, sr, si, pos, kk, b, imp);
-      float mu = RF(pair_mu, p), t = RF(pair_invweight, p);
-      float invw = (t + mu * mu * t) * 2.f * mu * mu / m.impratio;
-      float R = fmaxf(invw * (1.f - imp) / imp, RR_MINVAL);
-      int r = nla + 4 * k + c.lane;
-      c.row_id[r] = m.nlimit + 4 * cc + c.lane;
+    for (int q = 0; q < 5; q++) si[q] = RF(pair_solimp, 5 * p + q);
+    kbi(m.timestep, sr, si, pos, kk, b, imp);
+    float mu = RF(pair_mu, p), t = RF(pair_invweight, p);
+    float invw = (t + mu * mu * t) * 2.f * mu * mu / m.impratio;
+    float R = fmaxf(invw * (1.f - imp) / imp, RR_MINVAL);
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      int r = nla + 4 * k + q;
+      c.row_id[r] = m.nlimit + 4 * cc + q;
       c.row_D[r] = 1.f / R;
       c.row_aref[r] = kk * imp * pos;
       c.row_Jaref[r] = b;
@@ -1080,14 +1106,22 @@ RR_DEV void make_constraint(Ctx<NS> &c) {
     }
     for (int k = 0; k < nca; k++) {
       int cc = c.cact[k];
-      int len = c.cmeta[4 * k + 1], adr = c.cmeta[4 * k + 2];
-      const float *J = jblock<NS>(c, k);
-      float mu = RF(pair_mu, RI(con_pair, cc));
+      int p = RI(con_pair, cc);
+      int ld = RI(pair_lastdof, p);
+      int len = RI(dof_depth, ld) + 1, adr = RI(dof_rowadr, ld);
+      const float *ab = c.cab + 18 * cc;
+      float mu = RF(pair_mu, p);
       for (int t = c.lane; t < len; t += 32) {
         int d = RR_META_COL(RI(M_meta, adr + t));
+        const float *cd = c.cdof + 6 * d;
+        float j3[3];
+        for (int r3 = 0; r3 < 3; r3++) {
+          j3[r3] = 0.f;
+          for (int q = 0; q < 6; q++) j3[r3] += ab[6 * r3 + q] * cd[q];
+        }
         for (int q = 0; q < 4; q++) {
           float f = (q & 1) ? -mu : mu;
-          dJ[(m.nlimit + 4 * cc + q) * m.nv + d] = J[t] + J[(1 + (q >> 1)) * len + t] * f;
+          dJ[(m.nlimit + 4 * cc + q) * m.nv + d] = j3[0] + j3[1 + (q >> 1)] * f;
         }
       }
       if (c.lane < 4) dD[m.nlimit + 4 * cc + c.lane] = c.row_D[nla + 4 * k + c.lane];
@@ -1287,10 +1321,13 @@ RR_DEV void solve_constraints(Ctx<NS> &c) {
     }
     /* ---- _update_constraint + _update_gradient ---- */
     prev_cost = cost;
+    prof<NS>(c, RR_PROF_SOLVE_UPD);
     cost = constraint_cost<NS>(c, c.qacc, Ma, gauss, true);
     mul_jt<NS>(c, c.row_jv, c.qfrc_constraint);
+    prof<NS>(c, RR_PROF_CRB); /* profiling bucket "crb" = constraint_cost + J' f inside the solver */
     RR_FOR_S { grad[s] = Ma[s] - c.qfrc_smooth[s] - c.qfrc_constraint[s]; Mgrad[s] = grad[s]; }
     solve_ld<NS>(c, Mgrad);
+    prof<NS>(c, RR_PROF_VEL); /* profiling bucket "com_vel" = the M^-1 grad solve inside the solver */
     if (first) {
       RR_FOR_S search[s] = -Mgrad[s];
       first = false;
@@ -1445,10 +1482,15 @@ template <int NS>
 RR_DEV void env_run(const RRModelDev &m, const RRStepArgs &a, int env_in, int slot, float *sm, const int32_t *ti, const float *tf,
                     int lane) {
   const int env = env_in < a.B ? env_in : a.B - 1;
+  const long long t_begin = a.work ? RR_CLOCK() : 0;
   Ctx<NS> c(m, a, env, slot, sm, ti, tf, lane);
   c.live = env_in < a.B;
   if (!c.live) c.dbg = nullptr;
-  if (RR_WITH_DEBUG && a.prof) c.tprev = RR_CLOCK();
+  if (RR_WITH_DEBUG && a.prof) {
+    if (lane < RR_NPROF) c.prof_acc[lane] = 0.f;
+    __syncwarp();
+    c.tprev = RR_CLOCK();
+  }
   const size_t e = (size_t)env;
   /* ---- load state ---- */
 #pragma unroll 1
@@ -1553,11 +1595,13 @@ RR_DEV void env_run(const RRModelDev &m, const RRStepArgs &a, int env_in, int sl
     if (a.metrics) { a.metrics[3 * e] = pos_reward; a.metrics[3 * e + 1] = quadctrl; a.metrics[3 * e + 2] = alive; }
     if (a.wrap) { a.steps[e] = a.mode == RR_MODE_INIT ? 0.f : steps; a.truncation[e] = trunc; }
     if (a.niter) a.niter[e] = c.niter;
+    if (a.work) a.work[e] = (float)(RR_CLOCK() - t_begin - c.wait);
   }
   /* optional raw outputs that survive the solver phase */
   if (a.contact_dist && m.nefc) for (int i = lane; i < m.ncon; i += 32) a.contact_dist[e * m.ncon + i] = c.con_dist[i];
   if (a.qacc) RR_FOR_S { int i = lane + 32 * s; if (i < m.nv) a.qacc[e * m.nv + i] = c.qacc[s]; }
   prof<NS>(c, RR_PROF_EPILOGUE);
+  prof_flush<NS>(c);
 }
 
 }  // namespace RR_NS

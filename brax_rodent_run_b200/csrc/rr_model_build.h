@@ -214,6 +214,10 @@ inline void rr_host_model_build(RRHostModel &hm, const int32_t *dir, const int32
     if (t_sched_back.empty()) t_sched_back.push_back(0);
     if (t_sched_fwd.empty()) t_sched_fwd.push_back(0);
   }
+  /* solve_half(): rowadr | depth << 16 | ndesc << 24 */
+  t_dof_pack.resize(nv);
+  for (int i = 0; i < nv; i++) t_dof_pack[i] = t_dof_rowadr[i] | (t_dof_depth[i] << 16) | (t_dof_ndesc[i] << 24);
+  if (t_dof_pack.empty()) t_dof_pack.push_back(0);
   /* factor(): row width rounded up to a power of two (log2), for the lane-group split of short rows */
   t_dof_log2w.assign(nv, 5);
   for (int i = 0; i < nv; i++) {
@@ -252,8 +256,9 @@ inline void rr_host_model_build(RRHostModel &hm, const int32_t *dir, const int32
   cpF(t_pair_margin, RR_FID(pair_includemargin));
   t_pair_body.resize(np); t_pair_lastdof.resize(np); t_pair_gpos.resize(3 * np); t_pair_gquat.resize(4 * np);
   t_pair_size.resize(3 * np); t_pair_plane_n.resize(3 * np); t_pair_plane_p.resize(3 * np); t_pair_invweight.resize(np);
-  t_con_pair.assign(std::max(nc, 1), 0); t_con_Jadr.assign(std::max(nc, 1), 0);
-  int nJ = 0;
+  t_con_pair.assign(std::max(nc, 1), 0);
+  t_pair_cb.assign(std::max(np, 1), 0);
+  std::vector<int> cb_bodies; /* distinct bodies carrying a collision geom ("contact bodies") */
   for (int p = 0; p < np; p++) {
     int bp = gbody[g1[p]], b2 = gbody[g2[p]];
     if (lastdof[bp] >= 0) throw std::runtime_error("NotImplemented: collision plane on a moving body");
@@ -285,13 +290,22 @@ inline void rr_host_model_build(RRHostModel &hm, const int32_t *dir, const int32
     t_pair_lastdof[p] = lastdof[b2];
     t_pair_invweight[p] = (float)(binvw[2 * bp] + binvw[2 * b2]);
     int cend = (p + 1 < np) ? t_pair_conadr[p + 1] : nc;
-    for (int c = t_pair_conadr[p]; c < cend; c++) {
-      t_con_pair[c] = p;
-      t_con_Jadr[c] = nJ;
-      nJ += 3 * (t_dof_depth[lastdof[b2]] + 1);
-    }
+    for (int c = t_pair_conadr[p]; c < cend; c++) t_con_pair[c] = p;
+    auto it = std::find(cb_bodies.begin(), cb_bodies.end(), b2);
+    if (it == cb_bodies.end()) { cb_bodies.push_back(b2); it = cb_bodies.end() - 1; }
+    t_pair_cb[p] = (int)(it - cb_bodies.begin());
   }
-  d.nJ = nJ;
+  d.ncb = (int)cb_bodies.size();
+  for (int b : cb_bodies) t_cb_lastdof.push_back(lastdof[b]);
+  if (t_cb_lastdof.empty()) t_cb_lastdof.push_back(0);
+  /* static contact list of each contact body */
+  t_cb_conadr.assign(d.ncb + 1, 0);
+  for (int kb = 0; kb < d.ncb; kb++) {
+    t_cb_conadr[kb] = (int)t_cb_conlist.size();
+    for (int c = 0; c < nc; c++) if (t_pair_cb[t_con_pair[c]] == kb) t_cb_conlist.push_back(c);
+  }
+  t_cb_conadr[d.ncb] = (int)t_cb_conlist.size();
+  if (t_cb_conlist.empty()) t_cb_conlist.push_back(0);
 
   /* ---- joint limits ---- */
   const int32_t *ljnt = B.I(RR_FID(limit_jntid));
@@ -338,7 +352,7 @@ inline void rr_host_model_build(RRHostModel &hm, const int32_t *dir, const int32
   int o = 0;
   auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };
   s.qpos = take(nq); s.qvel = take(nv); s.act = take(d.na); s.ctrl = take(nu); s.actdot = take(d.na);
-  s.com = take(3 * d.nroot); s.vbuf = take(nv); s.Dinv = take(nv); s.xq1 = take(4);
+  s.com = take(3 * d.nroot); s.vbuf = take(nv); s.Dinv = take(nv); s.xq1 = take(4); s.prof_acc = take(16);
   s.M = take(nM); s.LD = take(nM);
   s.xpos = take(3 * nb); s.xquat = take(4 * nb); s.cdof = take(6 * nv);
   const int c0 = o;
@@ -349,21 +363,14 @@ inline void rr_host_model_build(RRHostModel &hm, const int32_t *dir, const int32
   int c1_end = o;
   o = c1b; s.crb = take(10 * nb); s.fcrb = s.crb;
   c1_end = std::max(c1_end, o);
-  /* C2: fixed part, then split what is left between Jacobian blocks and rows (5 arrays of capR) */
+  /* C2: contact arrays, then as many constraint rows (5 arrays) as fit in the recycled span */
   o = c0;
-  s.con_dist = take(nc); s.con_pos = take(3 * nc); s.con_frame = take(9 * nc); s.cact = take(nc); s.cmeta = take(4 * nc);
+  s.con_dist = take(nc); s.cab = take(18 * nc); s.cscr = take(3 * nc); s.cbv = take(6 * d.ncb); s.cact = take(nc); s.ckidx = take(nc);
   int avail = c1_end - o;
-  int capR = std::min(d.nefc, 96) & ~3;
+  int capR = std::min((d.nefc + 3) & ~3, std::max(avail / 5, 32) & ~3);
   if (capR < 4) capR = 4;
-  int capJ = avail - 5 * capR;
-  if (capJ < 3 * 40) { /* tiny models: grow the region instead */
-    capJ = std::min(nJ, 3 * 40 * 4);
-    capJ = (capJ + 3) & ~3;
-  }
-  capJ = std::min(capJ & ~3, (nJ + 3) & ~3);
-  if (capJ < 4) capJ = 4;
-  s.capJ = capJ; s.capR = capR;
-  s.con_J = take(capJ); s.row_D = take(5 * capR);
+  s.capR = capR;
+  s.row_D = take(5 * capR);
   s.total = std::max(c1_end, o);
 
   hm.obs_dim = nq + nv + 10 * (nb - 1) + 6 * (nb - 1) + nv + 3; /* Rodent_Env_Brax.py:149-158 */

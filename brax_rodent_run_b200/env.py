@@ -166,6 +166,7 @@ class Rodent:
         model: Union[str, mjcf.FlatModel, None] = None,
         xml_path: Optional[str] = None,
         kinematics_outputs: bool = True,
+        balance: bool = False,
         _lib_path: Optional[str] = None,
         **kwargs,
     ):
@@ -216,6 +217,36 @@ class Rodent:
             self._healthy_z_range[0], self._healthy_z_range[1], int(self._terminate_when_unhealthy)))
         self._episode_length = 0
         self._qpos0 = torch.from_numpy(self.sys.qpos0).to(self.device)
+        # load balancing: the warps of a CTA rendezvous every substep, so environments of similar cost (last step's
+        # cycle count) are grouped into the same CTA and the groups dealt to the CTAs in snake order
+        g, w, p = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+        _lib.check(self._L, self._L.rr_env_geometry(self._env, ctypes.byref(g), ctypes.byref(w), ctypes.byref(p)))
+        self._geometry = (g.value, w.value, p.value)
+        self._balance = bool(balance) and self.num_envs > w.value
+        self._slot_of_group = self._snake_slots() if self._balance else None
+
+    def _snake_slots(self) -> torch.Tensor:
+        """Slot index (length = ctas * passes groups of `envs_per_cta` slots) of the k-th most expensive group: pass 0
+        deals groups to CTAs 0..n-1, pass 1 in reverse, ... so every CTA gets a similar total."""
+        ctas, wpb, passes = self._geometry
+        order = []
+        for ps in range(passes):
+            ctas_order = range(ctas) if ps % 2 == 0 else range(ctas - 1, -1, -1)
+            order += [ps * ctas + c for c in ctas_order]
+        return torch.tensor(order, dtype=torch.long, device=self.device)
+
+    def _env_order(self, work: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+        if not self._balance or work is None:
+            return None
+        ctas, wpb, passes = self._geometry
+        nslots = ctas * wpb * passes
+        idx = torch.argsort(work, descending=True).to(torch.int32)
+        padded = torch.full((nslots,), -1, dtype=torch.int32, device=self.device)
+        padded[: self.num_envs] = idx
+        groups = padded.view(ctas * passes, wpb)                 # group k = k-th most expensive envs
+        out = torch.empty_like(groups)
+        out[self._slot_of_group] = groups                        # place group k at its (pass, cta) slot
+        return out.reshape(-1).contiguous()
 
     def __del__(self):
         L = getattr(self, "_L", None)
@@ -276,6 +307,8 @@ class Rodent:
             t.update(xpos=self._empty(B, d.nbody, 3), xquat=self._empty(B, d.nbody, 4), subtree_com=self._empty(B, d.nroot, 3))
         if self._episode_length:
             t.update(steps=self._empty(B), truncation=self._empty(B))
+        if self._balance:
+            t.update(work=self._empty(B))
         buf = _lib.RRBuffers()
         for k, v in t.items():
             setattr(buf, k, v.data_ptr())
@@ -353,8 +386,13 @@ class Rodent:
             buf.first_qpos, buf.first_qvel, buf.first_act = f.qpos.data_ptr(), f.qvel.data_ptr(), f.act.data_ptr()
             buf.first_qacc_warmstart, buf.first_time = f.qacc_warmstart.data_ptr(), f.time.data_ptr()
             buf.first_obs = state.info["first_obs"].data_ptr()
+        order = self._env_order(state.info.get("work"))
+        if order is not None:
+            buf.env_order = order.data_ptr()
         _lib.check(self._L, self._L.rr_env_step(self._env, ctypes.byref(buf), _ptr(action), self._n_frames, self._stream()))
         info["cur_frame"] = t["cur_frame"]
+        if self._balance:
+            info["work"] = t["work"]
         if self._episode_length:
             info["steps"], info["truncation"] = t["steps"], t["truncation"]
         return self._make_state(t, action, info)

@@ -69,6 +69,12 @@ typedef struct rr_buffers {
   float *contact_dist;    /* [B, ncon] */
   float *qacc;            /* [B, nv] */
   int32_t *solver_niter;  /* [B] */
+  /* Load balancing (optional).  work[B]: out, cycles this environment's warp spent in the step (a cost estimate for
+   * the next step).  env_order: in, slot -> environment index (-1 = idle slot), length rr_env_num_slots(); the warps of
+   * a CTA rendezvous every substep, so a caller that groups environments of similar cost into the same CTA (see
+   * Rodent._balance) shortens the wait.  Null = identity order. */
+  float *work;
+  const int32_t *env_order;
 } rr_buffers;
 
 const char *rr_last_error(void);
@@ -90,6 +96,9 @@ int rr_env_set_task(rr_env *e, const float *track_pos, int32_t track_len, float 
                     float healthy_z_lo, float healthy_z_hi, int32_t terminate_when_unhealthy);
 /* brax EpisodeWrapper(episode_length, action_repeat=1) + AutoResetWrapper fused into the step; 0 = off */
 int rr_env_set_wrappers(rr_env *e, int32_t episode_length);
+/* Launch geometry of the step kernel for this batch: CTAs, environments (warps) per CTA, passes per warp.  Slot p of
+ * env_order is pass * (ctas * envs_per_cta) + cta * envs_per_cta + warp. */
+int rr_env_geometry(const rr_env *e, int32_t *ctas, int32_t *envs_per_cta, int32_t *passes);
 
 /* pipeline_init + _get_obs of Rodent.reset (Rodent_Env_Brax.py:87-95): mjx.forward at (qpos, qvel) with
  * act = ctrl = 0 is the caller's job to zero; writes normalised qpos, qacc_warmstart, obs, zero reward/done/metrics. */

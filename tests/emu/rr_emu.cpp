@@ -126,6 +126,7 @@ static int rrb_h2d(void *dst, const void *src, size_t bytes, void *) { memcpy(ds
 static int rrb_d2h(void *dst, const void *src, size_t bytes, void *) { memcpy(dst, src, bytes); return 0; }
 static int rrb_sync(void *) { return 0; }
 static int rrb_num_slots() { return 1; }
+static int rrb_geometry(const RRModelDev &, int B, int *ctas, int *wpb) { *ctas = B; *wpb = 1; return 0; }
 
 struct EmuJob { const RRModelDev *m; const RRStepArgs *a; int env; float *sm; const int32_t *ti; const float *tf; };
 template <int NS>
@@ -135,7 +136,9 @@ static void emu_lane(int lane, void *arg) {
 }
 static int rrb_launch_step(const RRModelDev &m, const RRStepArgs &a, void *) {
   std::vector<float> sm((size_t)m.sm.total + 16);
-  for (int env = 0; env < a.B; env++) {
+  for (int slot = 0; slot < a.B; slot++) {
+    int env = a.env_order ? a.env_order[slot] : slot;
+    if (env < 0) continue;
     /* poison shared memory so that reads of unwritten slots show up as NaN */
     for (auto &x : sm) x = NAN;
     /* "shared memory" copies of the tables, as the CUDA kernel stages them */

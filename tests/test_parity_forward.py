@@ -64,10 +64,10 @@ def test_forward_intermediates(backend, model_name, iters, make_env, oracle_mod)
         # fewer iteration than the fp64 oracle; the result must agree regardless
         assert abs(int(out["scalars"][e, 0]) - int(o.scalar("solver_niter"))) <= 1
         # fp32 CG iterates (different summation order, FMA contraction) vs the fp64 oracle: accelerations to 5e-4,
-        # constraint forces (amplified by efc_D ~ 1e4) to 1e-3; the state-level bound (1e-4 on qpos / qvel after a
+        # constraint forces (amplified by efc_D ~ 1e4) to 3e-3; the state-level bound (1e-4 on qpos / qvel after a
         # step) is asserted in test_parity_step.py
         for k in POST_SOLVER:
-            tol = 5e-4 if k == "qacc" else 1e-3
+            tol = 5e-4 if k == "qacc" else 3e-3
             assert rel(out[k][e], o.get(k)) < tol, (k, e, rel(out[k][e], o.get(k)))
         assert rel(out["qacc_warmstart"][e], o.get("qacc_warmstart")) < 5e-4
 
