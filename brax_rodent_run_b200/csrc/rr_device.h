@@ -16,7 +16,7 @@
 #define RR_DEV_INT_TABLES(X)                                                                              \
   X(body_parentid) X(body_rootslot) X(body_jntadr) X(body_jntnum) X(level_adr) X(level_body)              \
   X(jnt_type) X(jnt_qposadr) X(jnt_dofadr) X(jnt_bodyid)                                                  \
-  X(dof_bodyid) X(dof_depth) X(dof_ndesc) X(dof_rowadr) X(dof_log2w) X(dof_pack) X(M_meta) X(sched_back) X(sched_fwd)                            \
+  X(dof_bodyid) X(dof_depth) X(dof_ndesc) X(dof_rowadr) X(dof_log2w) X(dof_pack) X(dof_cbmask) X(M_meta)                            \
   X(act_dofadr) X(act_qposadr) X(act_dyntype) X(act_gaintype) X(act_biastype) X(act_ctrllimited)          \
   X(act_forcelimited) X(act_actadr)                                                                       \
   X(pair_fn) X(pair_body) X(pair_conadr) X(pair_lastdof) X(pair_cb) X(cb_lastdof) X(cb_conadr) X(cb_conlist) X(con_pair)                          \
@@ -40,7 +40,7 @@
  *                                      observation slices are written to HBM before the solver in the last substep).
  */
 struct RRSmem {
-  int qpos, qvel, act, ctrl, actdot, com, vbuf, Dinv, xq1, prof_acc; /* A */
+  int qpos, qvel, act, ctrl, actdot, com, vbuf, xq1, prof_acc; /* A */
   int M, LD;                                               /* B */
   int xpos, xquat, cdof;                                   /* C, live through the Jacobian build */
   int cinert, qfrc_act, cvel, cacc, cfrc, crb, fcrb;       /* C1 */
@@ -52,7 +52,6 @@ struct RRSmem {
 struct RRModelDev {
   int nq, nv, nu, na, nbody, njnt, ngeom, nM, npair, ncon, nlimit, nefc, nlevel, nroot, ncb;
   int solver, iterations, ls_iterations;
-  int nsched_back, nsched_fwd; /* steps of the two-wide triangular-solve schedules */
   float timestep, gravity[3], tolerance, ls_tolerance, impratio, meaninertia;
   RRSmem sm;
   /* The tables live in two contiguous device buffers; the kernel stages both into shared memory once per CTA and

@@ -180,7 +180,7 @@ struct Ctx {
   int env, lane;
   const int32_t *ti; /* shared-memory copies of the model tables */
   const float *tf;
-  float *qpos, *qvel, *act, *ctrl, *actdot, *xpos, *xquat, *com, *cinert, *cdof, *cvel, *M, *LD, *Dinv, *vbuf, *qfrc_act;
+  float *qpos, *qvel, *act, *ctrl, *actdot, *xpos, *xquat, *com, *cinert, *cdof, *cvel, *M, *LD, *vbuf, *qfrc_act;
   float *crb, *fcrb, *cacc, *cfrc, *con_dist, *cab, *cscr, *cbv, *row_D, *row_aref, *row_Jaref, *row_jv;
   int *row_id, *cact, *ckidx;
   float *prof_acc; /* RR_NPROF per-stage cycle sums (debug builds) */
@@ -188,7 +188,8 @@ struct Ctx {
   float *sm_base, *grows; /* shared-memory base; global overflow for constraint rows */
   /* per-lane dof metadata: dof i = lane + 32 s */
   int radr[NS], dep[NS], nd[NS];
-  float dinv[NS];
+  float dinv[NS], dinv2[NS]; /* 1 / D of LD (M) and of the Euler factor (M + dt damping) */
+  float ma_warm[NS];         /* M qacc_warmstart, formed before M is factorised in place */
   /* register-resident nv-vectors */
   float qfrc_smooth[NS], qacc_smooth[NS], warm[NS], qacc[NS], qfrc_constraint[NS];
   int nla, nca; /* active limit rows, active contacts; rows = nla + 4 nca */
@@ -218,7 +219,7 @@ struct Ctx {
     prof_acc = sm + s.prof_acc;
     qpos = sm + s.qpos; qvel = sm + s.qvel; act = sm + s.act; ctrl = sm + s.ctrl; actdot = sm + s.actdot;
     xpos = sm + s.xpos; xquat = sm + s.xquat; com = sm + s.com; cinert = sm + s.cinert; cdof = sm + s.cdof;
-    cvel = sm + s.cvel; M = sm + s.M; LD = sm + s.LD; Dinv = sm + s.Dinv; vbuf = sm + s.vbuf; qfrc_act = sm + s.qfrc_act;
+    cvel = sm + s.cvel; M = sm + s.M; LD = sm + s.LD;  vbuf = sm + s.vbuf; qfrc_act = sm + s.qfrc_act;
     crb = sm + s.crb; fcrb = sm + s.fcrb; cacc = sm + s.cacc; cfrc = sm + s.cfrc;
     con_dist = sm + s.con_dist; cab = sm + s.cab; cscr = sm + s.cscr; cbv = sm + s.cbv;
     cact = (int *)(sm + s.cact);
@@ -231,7 +232,7 @@ struct Ctx {
       radr[s_] = v ? ti[m.o_dof_rowadr + i] : 0;
       dep[s_] = v ? ti[m.o_dof_depth + i] : 0;
       nd[s_] = v ? ti[m.o_dof_ndesc + i] : 0;
-      dinv[s_] = 0.f;
+      dinv[s_] = 0.f; dinv2[s_] = 0.f; ma_warm[s_] = 0.f;
     }
     nla = nca = 0;
     niter = 0;
@@ -511,120 +512,134 @@ RR_DEV void crb_and_mass_matrix(Ctx<NS> &c) {
   __syncwarp();
 }
 
-/* Tree-sparse L'DL factorisation of (M + diag_scale * damping) into LD / Dinv (the factorisation MuJoCo's
- * mj_factorM computes, leaves to root; equivalent to the dense Cholesky MJX runs, jax.scipy cho_factor, up to
- * rounding).  Gather form: row k is final once the rows of all its descendants j are,
+/* Tree-sparse L'DL factorisations (the factorisation MuJoCo's mj_factorM computes, leaves to root; equivalent to the
+ * dense Cholesky MJX runs, jax.scipy cho_factor, up to rounding) of BOTH matrices a substep needs, in one sweep:
+ *   LD  <- factor(M)                        (solver: M^-1 grad, qacc_smooth)
+ *   M   <- factor(M + dt diag(damping))     (implicit-damping Euler), in place over M, which is dead afterwards
+ * The two eliminations are independent, so interleaving them doubles the instruction-level parallelism of the
+ * latency-bound sweep (a lone warp spends ~1.1 k cycles per row either way).
+ * Gather form: row k is final once the rows of all its descendants j are,
  *   row_k[s] = M(k, a_s) - sum_j L(j, k) D_j L(j, a_s),   D_k = row_k[diag],   L(k, a_s) = row_k[s] / D_k,
- * with lane s accumulating entry s in a register (rows deeper than 32 take a second register) and the per-descendant
- * scalars w_j = L(j, k) D_j staged through vbuf. */
+ * lane s accumulates entry s in a register (rows deeper than 32 take a second register); the per-descendant scalars
+ * w_j = L(j, k) D_j are staged once per row.  On exit the diagonal slots hold 1 / D. */
 template <int NS>
-RR_DEV void factor(Ctx<NS> &c, float diag_scale) {
+RR_DEV void factor2(Ctx<NS> &c, float dt) {
   const RRModelDev &m = c.m;
-  float2 *stage = reinterpret_cast<float2 *>(c.cacc); /* (w_j, rowadr_j) per descendant; cacc is dead in both passes */
+  float4 *stage = reinterpret_cast<float4 *>(c.cacc); /* (w_j, w2_j, rowadr_j, -) per descendant; cacc is dead here */
+  float *LD = c.LD, *L2 = c.M;
   __syncwarp();
 #pragma unroll 1
   for (int k = m.nv - 1; k >= 0; k--) {
-    const int mk = RI(dof_depth, k), adr = RI(dof_rowadr, k), nd = RI(dof_ndesc, k);
+    const int pk = RI(dof_pack, k); /* rowadr | depth << 16 | ndesc << 24 */
+    const int adr = pk & 0xffff, mk = (pk >> 16) & 255, nd = (int)((unsigned)pk >> 24);
+    const float damp = dt * RF(dof_damping, k);
+    if (nd > 0) {
+      for (int jj = c.lane; jj < nd; jj += 32) {
+        const int pj = RI(dof_pack, k + 1 + jj), rj = pj & 0xffff, dj = (pj >> 16) & 255;
+        stage[jj] = make_float4(LD[rj + mk] * LD[rj + dj], L2[rj + mk] * L2[rj + dj], __int_as_float(rj), 0.f);
+      }
+    }
     if (mk < 32) {
       /* short rows leave lanes idle: split the descendants over G = 32 / W lane groups (W = row width rounded up to a
        * power of two) and add the partial sums with shuffles */
       const int lw = RI(dof_log2w, k), W = 1 << lw, G = 32 >> lw;
       const int s0 = c.lane & (W - 1), g = c.lane >> lw;
       const bool on = s0 <= mk;
-      float acc = 0.f;
-      if (g == 0 && on) {
-        acc = c.M[adr + s0];
-        if (s0 == mk && diag_scale != 0.f) acc += diag_scale * RF(dof_damping, k);
-      }
-      if (nd > 0) {
-        for (int jj = c.lane; jj < nd; jj += 32) {
-          int j = k + 1 + jj, rj = RI(dof_rowadr, j);
-          stage[jj] = make_float2(c.LD[rj + mk] * c.LD[rj + RI(dof_depth, j)], __int_as_float(rj));
-        }
-        __syncwarp();
+      const int so = on ? s0 : 0;
+      float acc = (g == 0 && on) ? L2[adr + so] : 0.f, acc2 = acc;
+      if (g == 0 && s0 == mk) acc2 += damp;
+      __syncwarp();
 #pragma unroll 4
-        for (int jj = g; jj < nd; jj += G) {
-          const float2 wr = stage[jj];
-          if (on) acc -= wr.x * c.LD[__float_as_int(wr.y) + s0];
-        }
-        for (int o = W; o < 32; o <<= 1) acc += __shfl_xor_sync(RR_FULL, acc, o);
+      for (int jj = g; jj < nd; jj += G) {
+        const float4 wr = stage[jj];
+        const int rj = __float_as_int(wr.z);
+        acc -= on ? wr.x * LD[rj + so] : 0.f;
+        acc2 -= on ? wr.y * L2[rj + so] : 0.f;
       }
-      const float dk = __shfl_sync(RR_FULL, acc, mk);
-      const float inv = 1.f / dk;
-      if (g == 0 && s0 < mk) c.LD[adr + s0] = acc * inv;
-      if (c.lane == 0) { c.LD[adr + mk] = dk; c.Dinv[k] = inv; }
+      for (int o = W; o < 32; o <<= 1) {
+        acc += __shfl_xor_sync(RR_FULL, acc, o);
+        acc2 += __shfl_xor_sync(RR_FULL, acc2, o);
+      }
+      const float dk = __shfl_sync(RR_FULL, acc, mk), dk2 = __shfl_sync(RR_FULL, acc2, mk);
+      const float inv = 1.f / dk, inv2 = 1.f / dk2;
+      if (g == 0 && s0 < mk) { LD[adr + s0] = acc * inv; L2[adr + s0] = acc2 * inv2; }
+      if (c.lane == 0) { LD[adr + mk] = dk; L2[adr + mk] = dk2; }
     } else {
-      /* rows of 33 .. 64 entries: two registers per lane */
+      /* rows of 33 .. 64 entries: two registers per lane and matrix */
       const int s0 = c.lane, s1 = c.lane + 32;
-      float acc0 = c.M[adr + s0], acc1 = 0.f;
-      if (s1 <= mk) acc1 = c.M[adr + s1];
-      if (s1 == mk && diag_scale != 0.f) acc1 += diag_scale * RF(dof_damping, k);
-      if (nd > 0) {
-        for (int jj = c.lane; jj < nd; jj += 32) {
-          int j = k + 1 + jj, rj = RI(dof_rowadr, j);
-          stage[jj] = make_float2(c.LD[rj + mk] * c.LD[rj + RI(dof_depth, j)], __int_as_float(rj));
-        }
-        __syncwarp();
+      const bool on1 = s1 <= mk;
+      const int so1 = on1 ? s1 : 0;
+      float a0 = L2[adr + s0], a1 = on1 ? L2[adr + so1] : 0.f, b0 = a0, b1 = a1;
+      if (s1 == mk) b1 += damp;
+      __syncwarp();
 #pragma unroll 2
-        for (int jj = 0; jj < nd; jj++) {
-          const float2 wr = stage[jj];
-          const int rj = __float_as_int(wr.y);
-          acc0 -= wr.x * c.LD[rj + s0];
-          if (s1 <= mk) acc1 -= wr.x * c.LD[rj + s1];
-        }
+      for (int jj = 0; jj < nd; jj++) {
+        const float4 wr = stage[jj];
+        const int rj = __float_as_int(wr.z);
+        a0 -= wr.x * LD[rj + s0];
+        b0 -= wr.y * L2[rj + s0];
+        a1 -= on1 ? wr.x * LD[rj + so1] : 0.f;
+        b1 -= on1 ? wr.y * L2[rj + so1] : 0.f;
       }
-      const float dk = __shfl_sync(RR_FULL, acc1, mk & 31);
-      const float inv = 1.f / dk;
-      c.LD[adr + s0] = acc0 * inv;
-      if (s1 < mk) c.LD[adr + s1] = acc1 * inv;
-      if (c.lane == 0) { c.LD[adr + mk] = dk; c.Dinv[k] = inv; }
+      const float dk = __shfl_sync(RR_FULL, a1, mk & 31), dk2 = __shfl_sync(RR_FULL, b1, mk & 31);
+      const float inv = 1.f / dk, inv2 = 1.f / dk2;
+      LD[adr + s0] = a0 * inv; L2[adr + s0] = b0 * inv2;
+      if (s1 < mk) { LD[adr + s1] = a1 * inv; L2[adr + s1] = b1 * inv2; }
+      if (c.lane == 0) { LD[adr + mk] = dk; L2[adr + mk] = dk2; }
     }
     __syncwarp();
   }
-  RR_FOR_S { int i = c.lane + 32 * s; c.dinv[s] = i < m.nv ? c.Dinv[i] : 0.f; }
+  /* diagonal slots: D -> 1 / D (what the solves multiply by) */
+  RR_FOR_S {
+    const int i = c.lane + 32 * s;
+    float d1 = 0.f, d2 = 0.f;
+    if (i < m.nv) {
+      const int e = c.radr[s] + c.dep[s];
+      d1 = 1.f / LD[e]; d2 = 1.f / L2[e];
+      LD[e] = d1; L2[e] = d2;
+    }
+    c.dinv[s] = d1; c.dinv2[s] = d2;
+  }
+  __syncwarp();
 }
 
-/* x <- (L' D L)^-1 x with x distributed over lanes (dof i = lane + 32 s); pure register / shuffle solve.
- * L(i, j) sits at rowadr[i] + depth[j].  Both substitutions follow a host-built schedule (rr_model_build.h) that issues
- * up to two mutually independent dofs (different branches of the tree) per step, critical path first: the tail chain
- * (24 dofs) + trunk (12) bound the step count at about nv / 2, which halves the dependent shuffle -> FMA chain. */
+/* One dof per step in index order, per-slot loops so that the broadcast register is a compile-time choice, no branch in
+ * the body and all metadata / coefficient loads independent of x: unrolled by 8 the only dependent chain left is
+ * shuffle -> FMA (-> next shuffle). */
 template <int NS>
-RR_DEV void solve_ld(Ctx<NS> &c, float (&x)[NS]) {
-  const RRModelDev &m = c.m;
-  /* Straight-line loop bodies (no branch on the optional second entry; 255 = none is folded into the predicate) so that
-   * the unrolled schedule / metadata / coefficient loads of later steps can be hoisted above the dependent
-   * shuffle -> FMA chain. */
-  /* backward: x <- L^-T x, leaves to root; step dof i updates its ancestors j: (unsigned)(i - j - 1) < ndesc[j] */
-#pragma unroll 4
-  for (int st = 0; st < m.nsched_back; st++) {
-    const int e = RI(sched_back, st), ia = e & 255, ib = (e >> 8) & 255;
-    const bool hb = ib != 255;
-    const int adra = RI(dof_rowadr, ia), adrb = RI(dof_rowadr, hb ? ib : 0);
-    const float xa = __shfl_sync(RR_FULL, vselect<NS>(x, ia >> 5), ia & 31);
-    const float xb = __shfl_sync(RR_FULL, vselect<NS>(x, ib >> 5), ib & 31);
-    RR_FOR_S {
-      const int j = c.lane + 32 * s;
-      const float la = ((unsigned)(ia - 1 - j) < (unsigned)c.nd[s]) ? c.LD[adra + c.dep[s]] : 0.f;
-      const float lb = (hb && (unsigned)(ib - 1 - j) < (unsigned)c.nd[s]) ? c.LD[adrb + c.dep[s]] : 0.f;
-      x[s] -= la * xa;
-      x[s] -= lb * xb;
+RR_DEV void solve_ld(Ctx<NS> &c, float (&x)[NS], const float *LDm, const float (&dinv)[NS]) {
+  const int nv = c.m.nv;
+  /* backward: x <- L^-T x, leaves to root; dof i updates its ancestors j: (unsigned)(i - j - 1) < ndesc[j] */
+#pragma unroll
+  for (int si = NS - 1; si >= 0; si--) {
+    const int top = (nv - 32 * si) < 32 ? (nv - 32 * si) : 32;
+#pragma unroll 8
+    for (int src = top - 1; src >= 0; src--) {
+      const int i = 32 * si + src;
+      const int adr = RI(dof_rowadr, i);
+      const float xi = __shfl_sync(RR_FULL, x[si], src);
+#pragma unroll
+      for (int s = 0; s <= si; s++) {
+        const float l = ((unsigned)(i - 1 - (c.lane + 32 * s)) < (unsigned)c.nd[s]) ? LDm[adr + c.dep[s]] : 0.f;
+        x[s] -= l * xi;
+      }
     }
   }
-  RR_FOR_S x[s] *= c.dinv[s];
-  /* forward: x <- L^-1 x, root to leaves; step dof j updates its descendants i: (unsigned)(i - j - 1) < ndesc[j] */
-#pragma unroll 4
-  for (int st = 0; st < m.nsched_fwd; st++) {
-    const int e = RI(sched_fwd, st), ja = e & 255, jb = (e >> 8) & 255;
-    const bool hb = jb != 255;
-    const int pa = RI(dof_pack, ja), pb = hb ? RI(dof_pack, jb) : 0; /* rowadr | depth << 16 | ndesc << 24 */
-    const float xa = __shfl_sync(RR_FULL, vselect<NS>(x, ja >> 5), ja & 31);
-    const float xb = __shfl_sync(RR_FULL, vselect<NS>(x, jb >> 5), jb & 31);
-    RR_FOR_S {
-      const int i = c.lane + 32 * s;
-      const float la = ((unsigned)(i - 1 - ja) < ((unsigned)pa >> 24)) ? c.LD[c.radr[s] + ((pa >> 16) & 255)] : 0.f;
-      const float lb = ((unsigned)(i - 1 - jb) < ((unsigned)pb >> 24)) ? c.LD[c.radr[s] + ((pb >> 16) & 255)] : 0.f;
-      x[s] -= la * xa;
-      x[s] -= lb * xb;
+  RR_FOR_S x[s] *= dinv[s];
+  /* forward: x <- L^-1 x, root to leaves; dof j updates its descendants i: (unsigned)(i - j - 1) < ndesc[j] */
+#pragma unroll
+  for (int sj = 0; sj < NS; sj++) {
+    const int top = (nv - 32 * sj) < 32 ? (nv - 32 * sj) : 32;
+#pragma unroll 8
+    for (int src = 0; src < top; src++) {
+      const int j = 32 * sj + src;
+      const int pk = RI(dof_pack, j); /* rowadr | depth << 16 | ndesc << 24 */
+      const float xj = __shfl_sync(RR_FULL, x[sj], src);
+#pragma unroll
+      for (int s = sj; s < NS; s++) {
+        const float l = ((unsigned)(c.lane + 32 * s - 1 - j) < ((unsigned)pk >> 24)) ? LDm[c.radr[s] + ((pk >> 16) & 255)] : 0.f;
+        x[s] -= l * xj;
+      }
     }
   }
 }
@@ -641,9 +656,9 @@ RR_DEV void mul_m(Ctx<NS> &c, float (&y)[NS], const float (&v)[NS]) {
     float acc = 0.f;
     if (i < m.nv) {
       int adr = c.radr[s];
-#pragma unroll 2
+#pragma unroll 8
       for (int t = 0; t <= c.dep[s]; t++) acc += c.M[adr + t] * c.vbuf[RR_META_COL(RI(M_meta, adr + t))];
-#pragma unroll 2
+#pragma unroll 8
       for (int k = i + 1; k <= i + c.nd[s]; k++) acc += c.M[RI(dof_rowadr, k) + c.dep[s]] * c.vbuf[k];
     }
     y[s] = acc;
@@ -982,10 +997,13 @@ RR_DEV void mul_jt(Ctx<NS> &c, const float *frc, float (&qfc)[NS]) {
     if (i < m.nv) {
       acc = c.vbuf[i];
       const float *cd = c.cdof + 6 * i;
-#pragma unroll 2
-      for (int kb = 0; kb < m.ncb; kb++) {
-        int ld = RI(cb_lastdof, kb);
-        if ((unsigned)(ld - i) <= (unsigned)c.nd[s]) {
+      /* contact bodies whose chain contains dof i: static 64-bit mask in two words */
+#pragma unroll
+      for (int w = 0; w < 2; w++) {
+        unsigned mask = (unsigned)RI(dof_cbmask, 2 * i + w);
+        while (mask) {
+          const int kb = 32 * w + __ffs(mask) - 1;
+          mask &= mask - 1;
           const float *F = c.cbv + 6 * kb;
           acc += cd[0] * F[0] + cd[1] * F[1] + cd[2] * F[2] + cd[3] * F[3] + cd[4] * F[4] + cd[5] * F[5];
         }
@@ -1179,10 +1197,14 @@ RR_DEV void ls_eval(Ctx<NS> &c, int nra, const float (&alpha)[NA], float g0, flo
   }
 }
 
-/* Given qacc (regs): Ma = M qacc, Jaref = J qacc - aref (rows, smem). */
+/* Given qacc (regs): Jaref = J qacc - aref (rows, smem).  Ma = M qacc comes from the caller: M qacc_warmstart was formed
+ * before M was factorised in place, and M qacc_smooth = qfrc_smooth (qacc_smooth solves exactly that system; MJX
+ * multiplies it out again, which differs by solve round-off only). */
 template <int NS>
-RR_DEV void ctx_init(Ctx<NS> &c, const float (&qacc)[NS], float (&Ma)[NS]) {
-  mul_m<NS>(c, Ma, qacc); /* leaves qacc staged in vbuf */
+RR_DEV void ctx_init(Ctx<NS> &c, const float (&qacc)[NS]) {
+  __syncwarp();
+  vstore<NS>(c, qacc, c.vbuf);
+  __syncwarp();
   mul_j<NS>(c, c.row_Jaref);
   int nra = c.nla + 4 * c.nca;
   for (int r = c.lane; r < nra; r += 32) c.row_Jaref[r] -= c.row_aref[r];
@@ -1227,8 +1249,11 @@ RR_DEV void solve_constraints(Ctx<NS> &c) {
     float cs = 0.f, cw = 0.f, g;
     for (int cand = 0; cand < 3; cand++) {
       if (cand == 2 && cw < cs) break;
-      RR_FOR_S c.qacc[s] = (cand == 1) ? c.warm[s] : c.qacc_smooth[s];
-      ctx_init<NS>(c, c.qacc, Ma);
+      RR_FOR_S {
+        c.qacc[s] = (cand == 1) ? c.warm[s] : c.qacc_smooth[s];
+        Ma[s] = (cand == 1) ? c.ma_warm[s] : c.qfrc_smooth[s];
+      }
+      ctx_init<NS>(c, c.qacc);
       if (cand == 2) break;
       float cst = constraint_cost<NS>(c, c.qacc, Ma, g, false);
       if (cand == 0) cs = cst; else cw = cst;
@@ -1326,7 +1351,7 @@ RR_DEV void solve_constraints(Ctx<NS> &c) {
     mul_jt<NS>(c, c.row_jv, c.qfrc_constraint);
     prof<NS>(c, RR_PROF_CRB); /* profiling bucket "crb" = constraint_cost + J' f inside the solver */
     RR_FOR_S { grad[s] = Ma[s] - c.qfrc_smooth[s] - c.qfrc_constraint[s]; Mgrad[s] = grad[s]; }
-    solve_ld<NS>(c, Mgrad);
+    solve_ld<NS>(c, Mgrad, c.LD, c.dinv);
     prof<NS>(c, RR_PROF_VEL); /* profiling bucket "com_vel" = the M^-1 grad solve inside the solver */
     if (first) {
       RR_FOR_S search[s] = -Mgrad[s];
@@ -1419,15 +1444,16 @@ RR_DEV void substep(Ctx<NS> &c, bool integrate, float &time) {
     prof<NS>(c, RR_PROF_SMOOTH);
   }
   if (c.last_substep) forward_outputs<NS>(c);
+  dbg_copy<NS>(c, RR_DBG_M, c.M, m.nM);
+  mul_m<NS>(c, c.ma_warm, c.warm); /* the only product with M the solver needs (see ctx_init) */
+  RR_CTA_SYNC_AT(2);
+  factor2<NS>(c, dt);
   for (int pass = 0; pass < 2; pass++) {
-    RR_CTA_SYNC_AT(2);
-    factor<NS>(c, pass ? dt : 0.f);
     float x[NS];
     RR_FOR_S x[s] = pass ? c.qfrc_smooth[s] + c.qfrc_constraint[s] : c.qfrc_smooth[s];
-    solve_ld<NS>(c, x);
+    if (pass) solve_ld<NS>(c, x, c.M, c.dinv2); else solve_ld<NS>(c, x, c.LD, c.dinv);
     prof<NS>(c, pass ? RR_PROF_EULER : RR_PROF_FACTOR);
     if (pass == 0) {
-      dbg_copy<NS>(c, RR_DBG_M, c.M, m.nM);
       dbg_copy<NS>(c, RR_DBG_LD, c.LD, m.nM);
       RR_FOR_S c.qacc_smooth[s] = x[s];
       dbg_vec<NS>(c, RR_DBG_QACC_SMOOTH, c.qacc_smooth);

@@ -166,55 +166,7 @@ inline void rr_host_model_build(RRHostModel &hm, const int32_t *dir, const int32
   t_M_meta.resize(t_M_colind.size());
   for (size_t e = 0; e < t_M_colind.size(); e++)
     t_M_meta[e] = nv ? (t_M_rowid[e] | (t_M_colind[e] << 8) | (t_dof_rowadr[t_M_colind[e]] << 16)) : 0;
-  /* solve_ld(): two-wide schedules.  backward (leaves -> root): a dof is ready once all its children are done, priority =
-   * number of ancestors (longest remaining path); forward (root -> leaves): ready once its parent is done, priority =
-   * height of the subtree below.  Ready dofs are never ancestor-related, so any two of them are independent. */
-  {
-    std::vector<int> nchild(nv, 0), height(nv, 0);
-    for (int i = nv - 1; i >= 0; i--) {
-      int p = dofparent[i];
-      if (p >= 0) { nchild[p]++; height[p] = std::max(height[p], height[i] + 1); }
-    }
-    auto run = [&](bool backward, std::vector<int32_t> &out) {
-      std::vector<int> pending(nv, 0), done(nv, 0), ready;
-      for (int i = 0; i < nv; i++) {
-        pending[i] = backward ? nchild[i] : (dofparent[i] >= 0 ? 1 : 0);
-        if (pending[i] == 0) ready.push_back(i);
-      }
-      auto prio = [&](int i) { return backward ? t_dof_depth[i] : height[i]; };
-      while (!ready.empty()) {
-        std::sort(ready.begin(), ready.end(), [&](int a, int b) { return prio(a) != prio(b) ? prio(a) > prio(b) : a < b; });
-        std::vector<int> pick;
-        for (size_t q = 0; q < ready.size() && pick.size() < 2; q++) pick.push_back(ready[q]);
-        ready.erase(ready.begin(), ready.begin() + pick.size());
-        /* dofs that do no work in this direction still release their dependants but take no slot */
-        std::vector<int> work;
-        for (int i : pick) {
-          bool has_work = backward ? t_dof_depth[i] > 0 : t_dof_ndesc[i] > 0;
-          if (has_work) work.push_back(i);
-        }
-        if (work.size() == 2) out.push_back(work[0] | (work[1] << 8));
-        else if (work.size() == 1) out.push_back(work[0] | (255 << 8));
-        for (int i : pick) {
-          done[i] = 1;
-          if (backward) {
-            int p = dofparent[i];
-            if (p >= 0 && --pending[p] == 0) ready.push_back(p);
-          } else {
-            for (int k = i + 1; k < nv; k++)
-              if (dofparent[k] == i && --pending[k] == 0) ready.push_back(k);
-          }
-        }
-      }
-    };
-    run(true, t_sched_back);
-    run(false, t_sched_fwd);
-    d.nsched_back = (int)t_sched_back.size();
-    d.nsched_fwd = (int)t_sched_fwd.size();
-    if (t_sched_back.empty()) t_sched_back.push_back(0);
-    if (t_sched_fwd.empty()) t_sched_fwd.push_back(0);
-  }
-  /* solve_half(): rowadr | depth << 16 | ndesc << 24 */
+  /* packed dof metadata: rowadr | depth << 16 | ndesc << 24 */
   t_dof_pack.resize(nv);
   for (int i = 0; i < nv; i++) t_dof_pack[i] = t_dof_rowadr[i] | (t_dof_depth[i] << 16) | (t_dof_ndesc[i] << 24);
   if (t_dof_pack.empty()) t_dof_pack.push_back(0);
@@ -298,6 +250,11 @@ inline void rr_host_model_build(RRHostModel &hm, const int32_t *dir, const int32
   d.ncb = (int)cb_bodies.size();
   for (int b : cb_bodies) t_cb_lastdof.push_back(lastdof[b]);
   if (t_cb_lastdof.empty()) t_cb_lastdof.push_back(0);
+  /* per dof: bit kb set when the chain of contact body kb contains the dof (mul_jt gathers only over these) */
+  if (d.ncb > 64) throw std::runtime_error("NotImplemented: more than 64 bodies with collision geoms");
+  t_dof_cbmask.assign(2 * std::max(nv, 1), 0);
+  for (int kb = 0; kb < d.ncb; kb++)
+    for (int dd = t_cb_lastdof[kb]; dd >= 0; dd = dofparent[dd]) t_dof_cbmask[2 * dd + (kb >> 5)] |= (int32_t)(1u << (kb & 31));
   /* static contact list of each contact body */
   t_cb_conadr.assign(d.ncb + 1, 0);
   for (int kb = 0; kb < d.ncb; kb++) {
@@ -352,7 +309,7 @@ inline void rr_host_model_build(RRHostModel &hm, const int32_t *dir, const int32
   int o = 0;
   auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };
   s.qpos = take(nq); s.qvel = take(nv); s.act = take(d.na); s.ctrl = take(nu); s.actdot = take(d.na);
-  s.com = take(3 * d.nroot); s.vbuf = take(nv); s.Dinv = take(nv); s.xq1 = take(4); s.prof_acc = take(16);
+  s.com = take(3 * d.nroot); s.vbuf = take(nv);  s.xq1 = take(4); s.prof_acc = take(16);
   s.M = take(nM); s.LD = take(nM);
   s.xpos = take(3 * nb); s.xquat = take(4 * nb); s.cdof = take(6 * nv);
   const int c0 = o;
