@@ -32,6 +32,10 @@ ENVS_PER_GPU = 4096
 N_FRAMES = 10
 ALGO_BYTES_PER_ENV_STEP = 7204  # state in/out + action + 1263-float obs + scalars
 FP32_PEAK_TFLOPS_NOMINAL = 148 * 128 * 2 * 1.965e9 / 1e12  # 74.4, no measured FP32 peak in MEASURED_PEAKS.json
+# dram__bytes_read.sum + dram__bytes_write.sum of one rr_step_kernel launch (profiles/r01_v9_ncu_raw.csv, `ncu --set full`):
+# 5.64 MB + 0.39 MB.  Below the algorithmic 29.5 MB because the 25 MB of state / observation written by a launch is still
+# resident in the 126 MB L2 when the kernel ends.
+NCU_DRAM_TRAFFIC_BYTES_PER_LAUNCH = 5_644_800 + 391_424
 
 
 def synthetic_track(n=250):
@@ -262,7 +266,7 @@ def run_b200(args):
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke},
             "gpu_launches": int(launches), "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": peak_gbs, "unit": "GB/s", "frac": achieved_gbs / peak_gbs,
-                         "traffic": None, "peak_source": peak_src, "kernel": "rr_step_kernel<3>",
+                         "traffic": NCU_DRAM_TRAFFIC_BYTES_PER_LAUNCH, "algorithmic_bytes": ALGO_BYTES_PER_ENV_STEP * B, "peak_source": peak_src, "kernel": "rr_step_kernel<3>",
                          "note": "the kernel is FP32-issue/latency bound, not HBM bound (SURVEY 8d); see roofline_fp32"},
             "roofline_fp32": {"achieved": achieved_tflops, "peak": FP32_PEAK_TFLOPS_NOMINAL, "unit": "TFLOP/s",
                               "frac": achieved_tflops / FP32_PEAK_TFLOPS_NOMINAL, "peak_source": "nominal 148 SM x 128 lanes x 2 x 1.965 GHz",
