@@ -14,7 +14,7 @@
 
 /* integer tables: name, expression for the element count (informative) */
 #define RR_DEV_INT_TABLES(X)                                                                              \
-  X(body_parentid) X(body_rootslot) X(body_jntadr) X(body_jntnum) X(level_adr) X(level_body)              \
+  X(body_parentid) X(body_eparent) X(body_rootslot) X(body_jntadr) X(body_jntnum) X(level_adr) X(level_body)              \
   X(jnt_type) X(jnt_qposadr) X(jnt_dofadr) X(jnt_bodyid)                                                  \
   X(dof_bodyid) X(dof_depth) X(dof_ndesc) X(dof_rowadr) X(dof_log2w) X(dof_pack) X(dof_cbmask) X(M_meta)                            \
   X(act_dofadr) X(act_qposadr) X(act_dyntype) X(act_gaintype) X(act_biastype) X(act_ctrllimited)          \
@@ -23,7 +23,7 @@
   X(limit_qposadr) X(limit_dofadr)
 
 #define RR_DEV_FLOAT_TABLES(X)                                                                            \
-  X(body_pos) X(body_quat) X(body_ipos) X(body_iquat) X(body_inertia) X(body_mass)                        \
+  X(body_epos) X(body_equat) X(body_ipos) X(body_iquat) X(body_inertia) X(body_mass)                        \
   X(jnt_pos) X(jnt_axis) X(jnt_stiffness) X(qpos0) X(qpos_spring)                                         \
   X(dof_armature) X(dof_damping)                                                                          \
   X(act_gear) X(act_dynprm) X(act_gainprm) X(act_biasprm) X(act_ctrlrange) X(act_forcerange)              \

@@ -341,12 +341,14 @@ RR_DEV void kinematics(Ctx<NS> &c) {
     int beg = RI(level_adr, lev), end = RI(level_adr, lev + 1);
     for (int idx = beg + c.lane; idx < end; idx += 32) {
       int b = RI(level_body, idx);
-      int p = RI(body_parentid, b);
+      /* effective parent = nearest ancestor that carries joints (or the world); body_epos / body_equat are the fixed
+       * offsets of the jointless bodies in between composed on the host, so a chain of welded bodies costs one level */
+      int p = RI(body_eparent, b);
       float ppos[3], pquat[4], bp[3], bq[4], pos[3], quat[4], r[3];
 #pragma unroll
-      for (int k = 0; k < 3; k++) { ppos[k] = c.xpos[3 * p + k]; bp[k] = RF(body_pos, 3 * b + k); }
+      for (int k = 0; k < 3; k++) { ppos[k] = c.xpos[3 * p + k]; bp[k] = RF(body_epos, 3 * b + k); }
 #pragma unroll
-      for (int k = 0; k < 4; k++) { pquat[k] = c.xquat[4 * p + k]; bq[k] = RF(body_quat, 4 * b + k); }
+      for (int k = 0; k < 4; k++) { pquat[k] = c.xquat[4 * p + k]; bq[k] = RF(body_equat, 4 * b + k); }
       rotq(r, bp, pquat);
 #pragma unroll
       for (int k = 0; k < 3; k++) pos[k] = ppos[k] + r[k];
@@ -679,7 +681,7 @@ RR_DEV void com_vel_and_rne(Ctx<NS> &c, float (&qfrc_bias)[NS]) {
     int beg = RI(level_adr, lev), end = RI(level_adr, lev + 1);
     for (int idx = beg + c.lane; idx < end; idx += 32) {
       int b = RI(level_body, idx);
-      int p = RI(body_parentid, b);
+      int p = RI(body_eparent, b); /* jointless bodies in between add nothing to cvel / cacc */
       float cv[6], ca[6];
 #pragma unroll
       for (int k = 0; k < 6; k++) { cv[k] = c.cvel[6 * p + k]; ca[k] = c.cacc[6 * p + k]; }

@@ -102,7 +102,7 @@ inline void rr_host_model_build(RRHostModel &hm, const int32_t *dir, const int32
   cpI(t_body_parentid, RR_FID(body_parentid));
   cpI(t_body_jntadr, RR_FID(body_jntadr));
   cpI(t_body_jntnum, RR_FID(body_jntnum));
-  cpF(t_body_pos, RR_FID(body_pos)); cpF(t_body_quat, RR_FID(body_quat)); cpF(t_body_ipos, RR_FID(body_ipos));
+  cpF(t_body_ipos, RR_FID(body_ipos));
   cpF(t_body_iquat, RR_FID(body_iquat)); cpF(t_body_inertia, RR_FID(body_inertia)); cpF(t_body_mass, RR_FID(body_mass));
   const int32_t *rootid = B.I(RR_FID(body_rootid)), *parent = B.I(RR_FID(body_parentid)), *lastdof = B.I(RR_FID(body_lastdof));
   /* kinematic-tree roots (world excluded): slot index per body; world gets slot 0 (its cinert is zero anyway) */
@@ -115,10 +115,35 @@ inline void rr_host_model_build(RRHostModel &hm, const int32_t *dir, const int32
     t_body_rootslot[b] = (int)(it - roots.begin());
   }
   d.nroot = std::max<int>(1, (int)roots.size());
-  /* tree levels (level 0 = world) */
+  /* effective parent (nearest ancestor with joints, or the world) and the composed fixed offset to it */
+  {
+    const double *bpos_d = B.F(RR_FID(body_pos)), *bquat_d = B.F(RR_FID(body_quat));
+    const int32_t *bjntnum = B.I(RR_FID(body_jntnum));
+    t_body_eparent.assign(nb, 0);
+    t_body_epos.assign(3 * nb, 0.f);
+    t_body_equat.assign(4 * nb, 0.f);
+    t_body_equat[0] = 1.f;
+    for (int b = 1; b < nb; b++) {
+      double pos[3] = {bpos_d[3 * b], bpos_d[3 * b + 1], bpos_d[3 * b + 2]};
+      double quat[4] = {bquat_d[4 * b], bquat_d[4 * b + 1], bquat_d[4 * b + 2], bquat_d[4 * b + 3]};
+      int p = parent[b];
+      while (p > 0 && bjntnum[p] == 0) { /* fold the welded parent's offset in: T_p o T_b */
+        double r[3], q[4];
+        quat_rot(r, pos, bquat_d + 4 * p);
+        for (int c = 0; c < 3; c++) pos[c] = bpos_d[3 * p + c] + r[c];
+        quat_mul(q, bquat_d + 4 * p, quat);
+        std::memcpy(quat, q, sizeof(q));
+        p = parent[p];
+      }
+      t_body_eparent[b] = p;
+      for (int c = 0; c < 3; c++) t_body_epos[3 * b + c] = (float)pos[c];
+      for (int c = 0; c < 4; c++) t_body_equat[4 * b + c] = (float)quat[c];
+    }
+  }
+  /* tree levels by effective depth (level 0 = world) */
   std::vector<int> depth(nb, 0);
   int maxd = 0;
-  for (int b = 1; b < nb; b++) { depth[b] = depth[parent[b]] + 1; maxd = std::max(maxd, depth[b]); }
+  for (int b = 1; b < nb; b++) { depth[b] = depth[t_body_eparent[b]] + 1; maxd = std::max(maxd, depth[b]); }
   d.nlevel = maxd + 1;
   t_level_adr.assign(d.nlevel + 1, 0);
   for (int lev = 1; lev <= maxd; lev++) {
