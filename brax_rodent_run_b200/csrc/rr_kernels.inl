@@ -527,14 +527,68 @@ RR_DEV void crb_and_mass_matrix(Ctx<NS> &c) {
 template <int NS>
 RR_DEV void factor2(Ctx<NS> &c, float dt) {
   const RRModelDev &m = c.m;
-  float4 *stage = reinterpret_cast<float4 *>(c.cacc); /* (w_j, w2_j, rowadr_j, -) per descendant; cacc is dead here */
+  float4 *stage = reinterpret_cast<float4 *>(c.cinert); /* per descendant (w_j, w2_j, rowadr_j, -) [x2 in paired steps]: up to
+                                                          8 (nv - 1) floats <= 10 nbody; cinert is dead here (its
+                                                          observation slice was stored by forward_outputs) */
   float *LD = c.LD, *L2 = c.M;
   __syncwarp();
 #pragma unroll 1
-  for (int k = m.nv - 1; k >= 0; k--) {
+  for (int k = m.nv - 1; k >= 0;) {
     const int pk = RI(dof_pack, k); /* rowadr | depth << 16 | ndesc << 24 */
     const int adr = pk & 0xffff, mk = (pk >> 16) & 255, nd = (int)((unsigned)pk >> 24);
     const float damp = dt * RF(dof_damping, k);
+    const int lwp = RI(dof_log2w, k); /* bits 0-7: log2 of the row width rounded up; bit 8: row k - 1 can ride along */
+    if (lwp & 256) {
+      /* Two rows per step.  k - 1 is the parent of k and has no other child, so its descendants are those of k plus k
+       * itself: both rows run over the same descendant rows (loaded once) and row k's own contribution to row k - 1 is
+       * applied from registers.  Halves the number of dependent steps along a chain. */
+      const int kp = k - 1, adrp = RI(dof_rowadr, kp);
+      const float dampp = dt * RF(dof_damping, kp);
+      const int lw = lwp & 255, W = 1 << lw, G = 32 >> lw;
+      const int s0 = c.lane & (W - 1), g = c.lane >> lw;
+      const bool onA = s0 <= mk, onB = s0 < mk; /* row k has mk + 1 entries, row k - 1 has mk */
+      const int soA = onA ? s0 : 0, soB = onB ? s0 : 0;
+      if (nd > 0) {
+        for (int jj = c.lane; jj < nd; jj += 32) {
+          const int pj = RI(dof_pack, k + 1 + jj), rj = pj & 0xffff, dj = (pj >> 16) & 255;
+          const float D1 = LD[rj + dj], D2 = L2[rj + dj];
+          stage[2 * jj] = make_float4(LD[rj + mk] * D1, L2[rj + mk] * D2, __int_as_float(rj), 0.f);
+          stage[2 * jj + 1] = make_float4(LD[rj + mk - 1] * D1, L2[rj + mk - 1] * D2, 0.f, 0.f);
+        }
+      }
+      float a1 = (g == 0 && onA) ? L2[adr + soA] : 0.f, a2 = a1;   /* row k:     LD / L2 accumulators */
+      float b1 = (g == 0 && onB) ? L2[adrp + soB] : 0.f, b2 = b1;  /* row k - 1 */
+      if (g == 0 && s0 == mk) a2 += damp;
+      if (g == 0 && s0 == mk - 1) b2 += dampp;
+      __syncwarp();
+#pragma unroll 2
+      for (int jj = g; jj < nd; jj += G) {
+        const float4 wa = stage[2 * jj], wb = stage[2 * jj + 1];
+        const int rj = __float_as_int(wa.z);
+        const float l1 = onA ? LD[rj + soA] : 0.f, l2 = onA ? L2[rj + soA] : 0.f;
+        a1 -= wa.x * l1; a2 -= wa.y * l2;
+        b1 -= onB ? wb.x * l1 : 0.f; b2 -= onB ? wb.y * l2 : 0.f;
+      }
+      for (int o = W; o < 32; o <<= 1) {
+        a1 += __shfl_xor_sync(RR_FULL, a1, o); a2 += __shfl_xor_sync(RR_FULL, a2, o);
+        b1 += __shfl_xor_sync(RR_FULL, b1, o); b2 += __shfl_xor_sync(RR_FULL, b2, o);
+      }
+      /* finish row k, fold it into row k - 1, finish row k - 1 */
+      const float dA1 = __shfl_sync(RR_FULL, a1, mk), dA2 = __shfl_sync(RR_FULL, a2, mk);
+      const float wk1 = __shfl_sync(RR_FULL, a1, mk - 1), wk2 = __shfl_sync(RR_FULL, a2, mk - 1); /* L(k, k-1) D_k */
+      const float iA1 = 1.f / dA1, iA2 = 1.f / dA2;
+      const float lA1 = a1 * iA1, lA2 = a2 * iA2;
+      b1 -= onB ? wk1 * lA1 : 0.f;
+      b2 -= onB ? wk2 * lA2 : 0.f;
+      const float dB1 = __shfl_sync(RR_FULL, b1, mk - 1), dB2 = __shfl_sync(RR_FULL, b2, mk - 1);
+      const float iB1 = 1.f / dB1, iB2 = 1.f / dB2;
+      if (g == 0 && s0 < mk) { LD[adr + s0] = lA1; L2[adr + s0] = lA2; }
+      if (g == 0 && s0 < mk - 1) { LD[adrp + s0] = b1 * iB1; L2[adrp + s0] = b2 * iB2; }
+      if (c.lane == 0) { LD[adr + mk] = dA1; L2[adr + mk] = dA2; LD[adrp + mk - 1] = dB1; L2[adrp + mk - 1] = dB2; }
+      __syncwarp();
+      k -= 2;
+      continue;
+    }
     if (nd > 0) {
       for (int jj = c.lane; jj < nd; jj += 32) {
         const int pj = RI(dof_pack, k + 1 + jj), rj = pj & 0xffff, dj = (pj >> 16) & 255;
@@ -544,7 +598,7 @@ RR_DEV void factor2(Ctx<NS> &c, float dt) {
     if (mk < 32) {
       /* short rows leave lanes idle: split the descendants over G = 32 / W lane groups (W = row width rounded up to a
        * power of two) and add the partial sums with shuffles */
-      const int lw = RI(dof_log2w, k), W = 1 << lw, G = 32 >> lw;
+      const int lw = lwp & 255, W = 1 << lw, G = 32 >> lw;
       const int s0 = c.lane & (W - 1), g = c.lane >> lw;
       const bool on = s0 <= mk;
       const int so = on ? s0 : 0;
@@ -590,6 +644,7 @@ RR_DEV void factor2(Ctx<NS> &c, float dt) {
       if (c.lane == 0) { LD[adr + mk] = dk; L2[adr + mk] = dk2; }
     }
     __syncwarp();
+    k--;
   }
   /* diagonal slots: D -> 1 / D (what the solves multiply by) */
   RR_FOR_S {

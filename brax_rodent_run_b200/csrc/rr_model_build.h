@@ -197,10 +197,20 @@ inline void rr_host_model_build(RRHostModel &hm, const int32_t *dir, const int32
   if (t_dof_pack.empty()) t_dof_pack.push_back(0);
   /* factor(): row width rounded up to a power of two (log2), for the lane-group split of short rows */
   t_dof_log2w.assign(nv, 5);
-  for (int i = 0; i < nv; i++) {
-    int lw = 0;
-    while ((1 << lw) < t_dof_depth[i] + 1 && lw < 5) lw++;
-    t_dof_log2w[i] = lw;
+  {
+    std::vector<int> nchild(nv, 0);
+    for (int i = 0; i < nv; i++) if (dofparent[i] >= 0) nchild[dofparent[i]]++;
+    for (int i = 0; i < nv; i++) {
+      int lw = 0;
+      while ((1 << lw) < t_dof_depth[i] + 1 && lw < 5) lw++;
+      /* bit 8: rows i and i - 1 can be eliminated in one step (i - 1 is i's parent and has no other child; the row fits
+       * one register per lane).  The sweep runs from nv - 1 down and takes pairs greedily from the leaf end of a chain. */
+      /* the staging area of factor2 is the (dead) cinert array: 10 nbody floats for 4 (8 when paired) floats per descendant */
+      if (4 * t_dof_ndesc[i] > 10 * nb) throw std::runtime_error("NotImplemented: more dofs below one dof than 2.5 x nbody");
+      bool pair = i >= 1 && dofparent[i] == i - 1 && nchild[i - 1] == 1 && t_dof_depth[i] >= 1 && t_dof_depth[i] < 32 &&
+                  8 * t_dof_ndesc[i] <= 10 * nb;
+      t_dof_log2w[i] = lw | (pair ? 256 : 0);
+    }
   }
   {
     int maxdep = 0;
