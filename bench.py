@@ -198,7 +198,7 @@ def run_b200(args):
     B, K, W = ENVS_PER_GPU, args.steps, args.warmup
     env = Rodent(synthetic_track(), num_envs=B, device=dev, model="rodent_0", solver="cg", iterations=args.iterations,
                  ls_iterations=args.ls_iterations, terminate_when_unhealthy=True, kinematics_outputs=False,
-                 balance=not args.no_balance)
+                 balance=args.balance)
     env.wrap_for_training(episode_length=1000)
     L = env._L
     gen = torch.Generator(device=dev)
@@ -325,7 +325,8 @@ def main():
     ap.add_argument("--iterations", type=int, default=8)      # brax_rodent_run_ppo.py:52
     ap.add_argument("--ls-iterations", type=int, default=8)   # brax_rodent_run_ppo.py:53
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-balance", action="store_true", help="disable cost-sorted env -> CTA assignment")
+    ap.add_argument("--balance", action="store_true",
+                    help="cost-sorted env -> CTA assignment (off: measured slower than the even contiguous split, see DESIGN.md)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -52,7 +52,8 @@
 #define RR_MV_RECURRENCE 1
 #endif
 #ifndef RR_SYNC_LEVEL
-#define RR_SYNC_LEVEL 2 /* 1: per substep; 2: + before each factorisation and the collision phase; 3: + per CG iteration */
+#define RR_SYNC_LEVEL 3 /* 1: per substep; 2: + before each factorisation and the collision phase; 3: + per CG iteration;
+                           4: + between the line search and the gradient update of an iteration */
 #endif
 /* the time spent waiting at the rendezvous is excluded from the per-environment work estimate (c.wait) */
 #define RR_CTA_SYNC_AT(level)                                 \
@@ -63,6 +64,13 @@
       if (c.a.work) c.wait += RR_CLOCK() - t_sync_;           \
     }                                                         \
   } while (0)
+
+/* unroll factor of the column loops of the triangular solves (code size vs. load pipelining) */
+#ifndef RR_SOLVE_UNROLL
+#define RR_SOLVE_UNROLL 8
+#endif
+#define RR_PRAGMA_(x) _Pragma(#x)
+#define RR_UNROLL(n) RR_PRAGMA_(unroll n)
 
 #define RR_FULL 0xffffffffu
 #define RR_MINVAL 1e-15f
@@ -670,7 +678,7 @@ RR_DEV void solve_ld(Ctx<NS> &c, float (&x)[NS], const float *LDm, const float (
 #pragma unroll
   for (int si = NS - 1; si >= 0; si--) {
     const int top = (nv - 32 * si) < 32 ? (nv - 32 * si) : 32;
-#pragma unroll 8
+RR_UNROLL(RR_SOLVE_UNROLL)
     for (int src = top - 1; src >= 0; src--) {
       const int i = 32 * si + src;
       const int adr = RI(dof_rowadr, i);
@@ -687,7 +695,7 @@ RR_DEV void solve_ld(Ctx<NS> &c, float (&x)[NS], const float *LDm, const float (
 #pragma unroll
   for (int sj = 0; sj < NS; sj++) {
     const int top = (nv - 32 * sj) < 32 ? (nv - 32 * sj) : 32;
-#pragma unroll 8
+RR_UNROLL(RR_SOLVE_UNROLL)
     for (int src = 0; src < top; src++) {
       const int j = 32 * sj + src;
       const int pk = RI(dof_pack, j); /* rowadr | depth << 16 | ndesc << 24 */
@@ -1324,17 +1332,17 @@ RR_DEV void solve_constraints(Ctx<NS> &c) {
 #pragma unroll 1
   for (int trip = 0; trip <= m.iterations; trip++) {
     RR_CTA_SYNC_AT(3);
-    if (finished) continue;
     float prev_grad[NS], prev_Mgrad[NS];
-    if (!first) {
+    if (!finished && !first) {
       if (m.iterations != 1) {
         float improvement = (prev_cost - cost) * scale;
         float gradient = sqrtf(vdot<NS>(grad, grad)) * scale;
-        if (niter >= m.iterations || improvement < m.tolerance || gradient < m.tolerance) { finished = true; continue; }
+        if (niter >= m.iterations || improvement < m.tolerance || gradient < m.tolerance) finished = true;
       } else if (niter >= 1) {
         finished = true;
-        continue;
       }
+    }
+    if (!finished && !first) {
       /* ---- linesearch ---- */
       float smag = sqrtf(vdot<NS>(search, search)) * m.meaninertia * nvf;
       float gtol = m.tolerance * m.ls_tolerance * smag;
@@ -1401,6 +1409,8 @@ RR_DEV void solve_constraints(Ctx<NS> &c) {
       RR_FOR_S { prev_grad[s] = grad[s]; prev_Mgrad[s] = Mgrad[s]; }
       prof<NS>(c, RR_PROF_SOLVE_LS);
     }
+    RR_CTA_SYNC_AT(4); /* the line searches end at different times; realign before the solve */
+    if (finished) continue;
     /* ---- _update_constraint + _update_gradient ---- */
     prev_cost = cost;
     prof<NS>(c, RR_PROF_SOLVE_UPD);
@@ -1560,6 +1570,21 @@ RR_DEV void substep(Ctx<NS> &c, bool integrate, float &time) {
   }
 }
 
+/* Padding pass of a persistent warp (its CTA has fewer environments than warps in this pass): run exactly the rendezvous
+ * sequence of substep() / solve_constraints() and nothing else, so the live warps of the CTA get the issue slots. */
+template <int NS>
+RR_DEV void substep_idle(Ctx<NS> &c, bool integrate) {
+  const RRModelDev &m = c.m;
+  RR_CTA_SYNC_AT(1);
+  RR_CTA_SYNC_AT(2); /* before the factorisations */
+  if (m.nefc != 0) {
+    RR_CTA_SYNC_AT(2); /* before the collision phase */
+#pragma unroll 1
+    for (int trip = 0; trip <= m.iterations; trip++) { RR_CTA_SYNC_AT(3); RR_CTA_SYNC_AT(4); }
+  }
+  (void)integrate;
+}
+
 /* ------------------------------------------------------------------------------------------ one environment */
 template <int NS>
 RR_DEV void env_run(const RRModelDev &m, const RRStepArgs &a, int env_in, int slot, float *sm, const int32_t *ti, const float *tf,
@@ -1592,6 +1617,10 @@ RR_DEV void env_run(const RRModelDev &m, const RRStepArgs &a, int env_in, int sl
   /* ---- physics ---- */
   {
     const int nrun = a.mode == RR_MODE_INIT ? 1 : a.nsub;
+    if (!c.live) {
+      for (int sub = 0; sub < nrun; sub++) substep_idle<NS>(c, a.mode != RR_MODE_INIT);
+      return;
+    }
     for (int sub = 0; sub < nrun; sub++) {
       c.last_substep = sub == nrun - 1;
       substep<NS>(c, a.mode != RR_MODE_INIT, time);
