@@ -55,14 +55,9 @@
 #define RR_SYNC_LEVEL 3 /* 1: per substep; 2: + before each factorisation and the collision phase; 3: + per CG iteration;
                            4: + between the line search and the gradient update of an iteration */
 #endif
-/* the time spent waiting at the rendezvous is excluded from the per-environment work estimate (c.wait) */
-#define RR_CTA_SYNC_AT(level)                                 \
-  do {                                                        \
-    if (RR_SYNC_LEVEL >= (level)) {                           \
-      const long long t_sync_ = c.a.work ? RR_CLOCK() : 0;    \
-      RR_CTA_SYNC();                                          \
-      if (c.a.work) c.wait += RR_CLOCK() - t_sync_;           \
-    }                                                         \
+#define RR_CTA_SYNC_AT(level)                \
+  do {                                       \
+    if (RR_SYNC_LEVEL >= (level)) RR_CTA_SYNC(); \
   } while (0)
 
 /* unroll factor of the column loops of the triangular solves (code size vs. load pipelining) */
@@ -204,7 +199,7 @@ struct Ctx {
   bool live;         /* false: padding pass of a persistent warp (keeps CTA barriers matched); no global stores */
   bool last_substep; /* the forward pass whose cinert / cvel / qfrc_actuator the observation reports */
   int niter;
-  long long wait; /* cycles spent at CTA rendezvous */
+  int niter_total; /* CG iterations over all substeps of this step: the load-balancing cost estimate */
   float *dbg;
   long long tprev;
 
@@ -246,7 +241,7 @@ struct Ctx {
     niter = 0;
     last_substep = false;
     live = true;
-    wait = 0;
+    niter_total = 0;
     dbg = a.dbg.buf ? a.dbg.buf + (size_t)env * a.dbg.stride : nullptr;
     tprev = 0;
   }
@@ -1309,6 +1304,15 @@ RR_DEV void solve_constraints(Ctx<NS> &c) {
   float Ma[NS], grad[NS], Mgrad[NS], search[NS], mv[NS];
   float gauss = 0.f, cost = INFINITY, prev_cost = INFINITY, beta = 0.f;
   RR_FOR_S mv[s] = 0.f;
+  int niter = 0;
+  bool first = true, finished = false;
+  if (nra == 0) {
+    /* no active row: the cost is the Gauss term alone, minimised (= 0) by qacc_smooth, which therefore wins the warm-start
+     * comparison and has zero gradient -- MJX leaves its loop before the first iteration with exactly this state */
+    RR_FOR_S { c.qacc[s] = c.qacc_smooth[s]; c.qfrc_constraint[s] = 0.f; }
+    cost = 0.f;
+    finished = true;
+  } else
   /* warm start: keep whichever of qacc_smooth / qacc_warmstart has the lower cost (candidate 2 = back to smooth) */
   {
     float cs = 0.f, cw = 0.f, g;
@@ -1325,8 +1329,6 @@ RR_DEV void solve_constraints(Ctx<NS> &c) {
     }
   }
   prof<NS>(c, RR_PROF_SOLVE_INIT);
-  int niter = 0;
-  bool first = true, finished = false;
   /* fixed trip count (iterations + 1 gradient updates at most) so that the CTA-wide rendezvous below stays matched
    * across warps; a warp whose solve has converged idles through the remaining trips */
 #pragma unroll 1
@@ -1438,6 +1440,7 @@ RR_DEV void solve_constraints(Ctx<NS> &c) {
     prof<NS>(c, RR_PROF_SOLVE_UPD);
   }
   c.niter = niter;
+  c.niter_total += niter;
   RR_FOR_S c.warm[s] = c.qacc[s];
   if (RR_WITH_DEBUG && c.dbg) {
     float *dF = c.dbg + dbg_offset(m, RR_DBG_EFC_FORCE), *dS = c.dbg + dbg_offset(m, RR_DBG_SCALARS);
@@ -1590,7 +1593,6 @@ template <int NS>
 RR_DEV void env_run(const RRModelDev &m, const RRStepArgs &a, int env_in, int slot, float *sm, const int32_t *ti, const float *tf,
                     int lane) {
   const int env = env_in < a.B ? env_in : a.B - 1;
-  const long long t_begin = a.work ? RR_CLOCK() : 0;
   Ctx<NS> c(m, a, env, slot, sm, ti, tf, lane);
   c.live = env_in < a.B;
   if (!c.live) c.dbg = nullptr;
@@ -1707,7 +1709,7 @@ RR_DEV void env_run(const RRModelDev &m, const RRStepArgs &a, int env_in, int sl
     if (a.metrics) { a.metrics[3 * e] = pos_reward; a.metrics[3 * e + 1] = quadctrl; a.metrics[3 * e + 2] = alive; }
     if (a.wrap) { a.steps[e] = a.mode == RR_MODE_INIT ? 0.f : steps; a.truncation[e] = trunc; }
     if (a.niter) a.niter[e] = c.niter;
-    if (a.work) a.work[e] = (float)(RR_CLOCK() - t_begin - c.wait);
+    if (a.work) a.work[e] = (float)c.niter_total;
   }
   /* optional raw outputs that survive the solver phase */
   if (a.contact_dist && m.nefc) for (int i = lane; i < m.ncon; i += 32) a.contact_dist[e * m.ncon + i] = c.con_dist[i];

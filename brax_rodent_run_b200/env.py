@@ -226,27 +226,30 @@ class Rodent:
         self._slot_of_group = self._snake_slots() if self._balance else None
 
     def _snake_slots(self) -> torch.Tensor:
-        """Slot index (length = ctas * passes groups of `envs_per_cta` slots) of the k-th most expensive group: pass 0
-        deals groups to CTAs 0..n-1, pass 1 in reverse, ... so every CTA gets a similar total."""
+        """Slot filled by the k-th most expensive environment.  Environments of similar cost share a CTA pass (the warps
+        of a CTA rendezvous, so a pass costs its slowest environment); groups are dealt to the CTAs in snake order (pass 0
+        CTA 0..n-1, pass 1 in reverse, ...) so that every CTA gets a similar total, and the short last pass is spread
+        evenly over the CTAs (idle warps only run the barriers)."""
         ctas, wpb, passes = self._geometry
-        order = []
+        B = self.num_envs
+        last = B - ctas * wpb * (passes - 1)           # environments in the last pass
+        slots = []
         for ps in range(passes):
             ctas_order = range(ctas) if ps % 2 == 0 else range(ctas - 1, -1, -1)
-            order += [ps * ctas + c for c in ctas_order]
-        return torch.tensor(order, dtype=torch.long, device=self.device)
+            for c in ctas_order:
+                cap = wpb if ps < passes - 1 else (last * (c + 1)) // ctas - (last * c) // ctas
+                slots += [ps * ctas * wpb + c * wpb + w for w in range(cap)]
+        assert len(slots) == B
+        return torch.tensor(slots, dtype=torch.long, device=self.device)
 
     def _env_order(self, work: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
         if not self._balance or work is None:
             return None
         ctas, wpb, passes = self._geometry
-        nslots = ctas * wpb * passes
         idx = torch.argsort(work, descending=True).to(torch.int32)
-        padded = torch.full((nslots,), -1, dtype=torch.int32, device=self.device)
-        padded[: self.num_envs] = idx
-        groups = padded.view(ctas * passes, wpb)                 # group k = k-th most expensive envs
-        out = torch.empty_like(groups)
-        out[self._slot_of_group] = groups                        # place group k at its (pass, cta) slot
-        return out.reshape(-1).contiguous()
+        out = torch.full((ctas * wpb * passes,), -1, dtype=torch.int32, device=self.device)
+        out[self._slot_of_group] = idx
+        return out
 
     def __del__(self):
         L = getattr(self, "_L", None)

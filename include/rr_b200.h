@@ -69,8 +69,8 @@ typedef struct rr_buffers {
   float *contact_dist;    /* [B, ncon] */
   float *qacc;            /* [B, nv] */
   int32_t *solver_niter;  /* [B] */
-  /* Load balancing (optional).  work[B]: out, cycles this environment's warp spent in the step (a cost estimate for
-   * the next step).  env_order: in, slot -> environment index (-1 = idle slot), length rr_env_num_slots(); the warps of
+  /* Load balancing (optional).  work[B]: out, CG iterations this environment's solver ran over the substeps of the step (a cost
+   * estimate for the next step).  env_order: in, slot -> environment index (-1 = idle slot), length rr_env_num_slots(); the warps of
    * a CTA rendezvous every substep, so a caller that groups environments of similar cost into the same CTA (see
    * Rodent._balance) shortens the wait.  Null = identity order. */
   float *work;

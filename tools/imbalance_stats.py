@@ -40,3 +40,23 @@ def grp(x, order):
 nat = np.arange(B)
 print("within-group-of-10 max/mean of solver-side cost: natural %.3f, sorted by previous step %.3f, sorted by itself %.3f" %
       (grp(sv[1], nat), grp(sv[1], np.argsort(sv[0])), grp(sv[1], np.argsort(sv[1]))))
+print("per-bucket cycles/env-step across environments (one step): p10 / p50 / p90")
+for i, nm in enumerate(names):
+    x = per_step[1][:, i]
+    print("  %-20s %10.0f %10.0f %10.0f" % (nm, np.percentile(x, 10), np.percentile(x, 50), np.percentile(x, 90)))
+x = per_step[1].sum(1)
+print("  %-20s %10.0f %10.0f %10.0f" % ("total", np.percentile(x, 10), np.percentile(x, 50), np.percentile(x, 90)))
+# solver iterations of the last substep
+import ctypes as C
+buf, t = env._out_buffers()
+nit = torch.zeros(B, dtype=torch.int32, device="cuda:0")
+env2 = env
+orig = env._out_buffers
+def patched():
+    b, tt = orig()
+    b.solver_niter = nit.data_ptr()
+    return b, tt
+env._out_buffers = patched
+s = env.step(s, torch.rand((B, env.action_size), device="cuda:0") * 2 - 1)
+torch.cuda.synchronize()
+print("solver iterations (last substep) histogram:", np.bincount(nit.cpu().numpy(), minlength=10).tolist())
