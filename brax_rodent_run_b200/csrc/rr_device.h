@@ -56,6 +56,10 @@ struct RRModelDev {
   RRSmem sm;
   /* The tables live in two contiguous device buffers; the kernel stages both into shared memory once per CTA and
    * indexes them through the element offsets o_<table> below (RI / RF macros in rr_kernels.inl). */
+  /* Per-dof layout word (rowadr | depth << 16 | ndesc << 24) by value: the struct is a __grid_constant__ kernel
+   * parameter, so kdof_pack[i] with a warp-uniform i is a constant-bank load into a uniform register -- the solve loops
+   * index it once per column without touching the LSU or vector registers.  Zero beyond nv (columns that do nothing). */
+  int32_t kdof_pack[160];
   const int32_t *ibuf;
   const float *fbuf;
   int ni, nf; /* element counts of ibuf / fbuf (multiples of 4) */

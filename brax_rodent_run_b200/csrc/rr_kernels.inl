@@ -664,24 +664,29 @@ RR_DEV void factor2(Ctx<NS> &c, float dt) {
 }
 
 /* One dof per step in index order, per-slot loops so that the broadcast register is a compile-time choice, no branch in
- * the body and all metadata / coefficient loads independent of x: unrolled by 8 the only dependent chain left is
- * shuffle -> FMA (-> next shuffle). */
+ * the body and all metadata / coefficient loads independent of x: the only dependent chain left is shuffle -> FMA
+ * (-> next shuffle).  The per-column layout word comes from the constant bank (kdof_pack) into uniform registers, the
+ * coefficient address is a per-lane pointer plus that uniform offset, and slots other than the last run a fixed 32
+ * columns (columns beyond nv have an all-zero layout word and update nothing), so a column costs the shuffle plus
+ * compare / predicated load / predicated FMA per slot. */
 template <int NS>
 RR_DEV void solve_ld(Ctx<NS> &c, float (&x)[NS], const float *LDm, const float (&dinv)[NS]) {
   const int nv = c.m.nv;
+  const float *lcol[NS], *lrow[NS]; /* &L(., lane dof) within a row; row of the lane dof */
+  unsigned nj[NS];                  /* -1 - lane dof: (i - 1 - j) = i + nj */
+  RR_FOR_S { lcol[s] = LDm + c.dep[s]; lrow[s] = LDm + c.radr[s]; nj[s] = (unsigned)(-1 - (c.lane + 32 * s)); }
   /* backward: x <- L^-T x, leaves to root; dof i updates its ancestors j: (unsigned)(i - j - 1) < ndesc[j] */
 #pragma unroll
   for (int si = NS - 1; si >= 0; si--) {
-    const int top = (nv - 32 * si) < 32 ? (nv - 32 * si) : 32;
+    const int top = si == NS - 1 ? ((nv - 32 * si) < 32 ? (nv - 32 * si) : 32) : 32;
 RR_UNROLL(RR_SOLVE_UNROLL)
     for (int src = top - 1; src >= 0; src--) {
       const int i = 32 * si + src;
-      const int adr = RI(dof_rowadr, i);
+      const int adr = c.m.kdof_pack[i] & 0xffff;
       const float xi = __shfl_sync(RR_FULL, x[si], src);
 #pragma unroll
       for (int s = 0; s <= si; s++) {
-        const float l = ((unsigned)(i - 1 - (c.lane + 32 * s)) < (unsigned)c.nd[s]) ? LDm[adr + c.dep[s]] : 0.f;
-        x[s] -= l * xi;
+        if ((unsigned)i + nj[s] < (unsigned)c.nd[s]) x[s] -= lcol[s][adr] * xi;
       }
     }
   }
@@ -689,16 +694,16 @@ RR_UNROLL(RR_SOLVE_UNROLL)
   /* forward: x <- L^-1 x, root to leaves; dof j updates its descendants i: (unsigned)(i - j - 1) < ndesc[j] */
 #pragma unroll
   for (int sj = 0; sj < NS; sj++) {
-    const int top = (nv - 32 * sj) < 32 ? (nv - 32 * sj) : 32;
+    const int top = sj == NS - 1 ? ((nv - 32 * sj) < 32 ? (nv - 32 * sj) : 32) : 32;
 RR_UNROLL(RR_SOLVE_UNROLL)
     for (int src = 0; src < top; src++) {
       const int j = 32 * sj + src;
-      const int pk = RI(dof_pack, j); /* rowadr | depth << 16 | ndesc << 24 */
+      const unsigned pk = (unsigned)c.m.kdof_pack[j]; /* rowadr | depth << 16 | ndesc << 24 */
+      const unsigned ndj = pk >> 24, dpj = (pk >> 16) & 255;
       const float xj = __shfl_sync(RR_FULL, x[sj], src);
 #pragma unroll
       for (int s = sj; s < NS; s++) {
-        const float l = ((unsigned)(c.lane + 32 * s - 1 - j) < ((unsigned)pk >> 24)) ? LDm[c.radr[s] + ((pk >> 16) & 255)] : 0.f;
-        x[s] -= l * xj;
+        if ((unsigned)(c.lane + 32 * s - 1 - j) < ndj) x[s] -= lrow[s][dpj] * xj;
       }
     }
   }

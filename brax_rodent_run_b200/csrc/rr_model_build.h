@@ -194,6 +194,7 @@ inline void rr_host_model_build(RRHostModel &hm, const int32_t *dir, const int32
   /* packed dof metadata: rowadr | depth << 16 | ndesc << 24 */
   t_dof_pack.resize(nv);
   for (int i = 0; i < nv; i++) t_dof_pack[i] = t_dof_rowadr[i] | (t_dof_depth[i] << 16) | (t_dof_ndesc[i] << 24);
+  for (int i = 0; i < 160; i++) d.kdof_pack[i] = i < nv ? t_dof_pack[i] : 0;
   if (t_dof_pack.empty()) t_dof_pack.push_back(0);
   /* factor(): row width rounded up to a power of two (log2), for the lane-group split of short rows */
   t_dof_log2w.assign(nv, 5);
