@@ -46,11 +46,11 @@ def synthetic_track(n=250):
 _W = {}
 
 
-def _oracle_init(iterations, ls_iterations):
+def _oracle_init(iterations, ls_iterations, model="rodent_0"):
     """Pool initializer: one oracle environment per worker process (kept alive across bench steps)."""
     from brax_rodent_run_b200 import mjcf, model_blob
     from oracle import oracle
-    m = mjcf.FlatModel.load(os.path.join(ROOT, "brax_rodent_run_b200", "assets", "rodent_0.npz"))
+    m = mjcf.FlatModel.load(os.path.join(ROOT, "brax_rodent_run_b200", "assets", f"{model}.npz"))
     blob = model_blob.pack(m)
     env = oracle.OracleRodentEnv(blob, (m.nq, m.nv, m.nu, m.nbody), synthetic_track(), iterations=iterations,
                                  ls_iterations=ls_iterations, precision="f32")
@@ -83,11 +83,12 @@ class OraclePool:
     """One oracle environment per host core; `rate(n)` steps every environment n times and returns env-steps/s with the
     slowest worker bounding the time (process start-up and model load excluded)."""
 
-    def __init__(self, iterations, ls_iterations, cores=None):
+    def __init__(self, iterations, ls_iterations, cores=None, model="rodent_0"):
         from oracle import oracle
         oracle.build()
         self.cores = cores or os.cpu_count() or 1
-        self.pool = mp.get_context("spawn").Pool(self.cores, initializer=_oracle_init, initargs=(iterations, ls_iterations))
+        self.pool = mp.get_context("spawn").Pool(self.cores, initializer=_oracle_init,
+                                                  initargs=(iterations, ls_iterations, model))
 
     def rate(self, n_steps):
         times = self.pool.map(_oracle_steps, [n_steps] * self.cores, chunksize=1)
@@ -103,7 +104,7 @@ def run_reference(args):
     if rank != 0:
         return
     n = 25  # env steps per core per bench "step": a bounded sample of the 4096-env workload (~0.15 s of CPU per core)
-    pool = OraclePool(args.iterations, args.ls_iterations)
+    pool = OraclePool(args.iterations, args.ls_iterations, model=args.model)
     for _ in range(args.warmup):
         pool.rate(n)
     total_t, t0 = 0.0, time.perf_counter()
@@ -114,7 +115,7 @@ def run_reference(args):
     cores = pool.cores
     pool.close()
     value = cores * n * args.steps / total_t
-    sample = (f"{cores} envs (one per host core) x {n} env steps per bench step, rodent_0.xml, oracle fp32 C restatement of the "
+    sample = (f"{cores} envs (one per host core) x {n} env steps per bench step, {args.model}.xml, oracle fp32 C restatement of the "
               "MJX step")
     print(json.dumps({
         "impl": "reference", "metric": "rodent env-steps/s", "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
@@ -130,11 +131,11 @@ def run_reference(args):
 
 
 def workload_config(args):
-    return {"workload": "rodent_0.xml run task, Rodent.step (10 substeps of 2 ms, CG solver) with random actions, "
-                        f"{ENVS_PER_GPU} envs/GPU", "envs_per_gpu": ENVS_PER_GPU, "n_frames": N_FRAMES, "solver": "cg",
+    return {"workload": f"{args.model}.xml run task, Rodent.step (10 substeps of 2 ms, CG solver) with random actions, "
+                        f"{args.envs} envs/GPU", "envs_per_gpu": args.envs, "n_frames": N_FRAMES, "solver": "cg",
             "iterations": args.iterations, "ls_iterations": args.ls_iterations, "episode_length": 1000,
             "terminate_when_unhealthy": True, "l2": "flushed between timed steps (256 MiB write outside the event pair)",
-            "includes": "physics + reward/done/metrics + 1263-float obs + fused Episode/AutoReset wrappers"}
+            "includes": "physics + reward/done/metrics + observation + fused Episode/AutoReset wrappers"}
 
 
 # ------------------------------------------------------------------------------------------------ clocks sampler
@@ -195,8 +196,8 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    B, K, W = ENVS_PER_GPU, args.steps, args.warmup
-    env = Rodent(synthetic_track(), num_envs=B, device=dev, model="rodent_0", solver="cg", iterations=args.iterations,
+    B, K, W = args.envs, args.steps, args.warmup
+    env = Rodent(synthetic_track(), num_envs=B, device=dev, model=args.model, solver="cg", iterations=args.iterations,
                  ls_iterations=args.ls_iterations, terminate_when_unhealthy=True, kinematics_outputs=False,
                  balance=args.balance)
     env.wrap_for_training(episode_length=1000)
@@ -285,7 +286,10 @@ def run_b200(args):
             pass
         peak_gbs, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)") if "hbm_gbs" in peaks else (6650.0, "fallback")
         kernel_ms = total_ms / K  # one rr_step_kernel launch per step; the event pair brackets only that launch
-        achieved_gbs = ALGO_BYTES_PER_ENV_STEP * B / (kernel_ms * 1e-3) / 1e9
+        d_ = env.dims  # state in + action in, state out + observation + 8 scalars out
+        algo_bytes = 4 * (2 * (d_.nq + 2 * d_.nv + d_.na) + env.action_size + d_.obs_dim + 8)
+        assert args.model != "rodent_0" or algo_bytes == ALGO_BYTES_PER_ENV_STEP
+        achieved_gbs = algo_bytes * B / (kernel_ms * 1e-3) / 1e9
         flops_per_env_step = 10 * (182e3 + args.iterations * (22962 + 1421 * (2 + 3 * args.ls_iterations)))
         achieved_tflops = flops_per_env_step * B / (kernel_ms * 1e-3) / 1e12
         out = {
@@ -295,23 +299,78 @@ def run_b200(args):
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke},
             "gpu_launches": int(launches), "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": peak_gbs, "unit": "GB/s", "frac": achieved_gbs / peak_gbs,
-                         "traffic": NCU_DRAM_TRAFFIC_BYTES_PER_LAUNCH, "algorithmic_bytes": ALGO_BYTES_PER_ENV_STEP * B, "peak_source": peak_src, "kernel": "rr_step_kernel<3>",
+                         "traffic": NCU_DRAM_TRAFFIC_BYTES_PER_LAUNCH if (args.model, B) == ("rodent_0", ENVS_PER_GPU) else None,
+                         "algorithmic_bytes": algo_bytes * B, "peak_source": peak_src, "kernel": "rr_step_kernel<3>" if d_.nv <= 96 else "rr_step_kernel<5>",
                          "note": "the kernel is FP32-issue/latency bound, not HBM bound (SURVEY 8d); see roofline_fp32"},
             "roofline_fp32": {"achieved": achieved_tflops, "peak": FP32_PEAK_TFLOPS_NOMINAL, "unit": "TFLOP/s",
                               "frac": achieved_tflops / FP32_PEAK_TFLOPS_NOMINAL, "peak_source": "nominal 148 SM x 128 lanes x 2 x 1.965 GHz",
                               "flops_per_env_step": flops_per_env_step, "flops_source": "SURVEY 8(d) dense-row operation-count estimate (upper bound: the kernel skips inactive rows)"},
             "wall_s": wall, "done_frac_last_step": done_frac,
         }
+        if args.model != "rodent_0":
+            out.pop("roofline_fp32")  # the operation-count estimate is rodent_0's
         if world == 1 and not args.no_cpu_baseline:
-            pool = OraclePool(args.iterations, args.ls_iterations)
+            pool = OraclePool(args.iterations, args.ls_iterations, model=args.model)
             pool.rate(5)
             rate, _ = pool.rate(150)
             cores = pool.cores
             pool.close()
             out["cpu_baseline"] = {"value": rate, "unit": "env-steps/s", "cores": cores, "kind": "port",
-                                   "sample": f"{cores} envs (one per host core) x 150 env steps, rodent_0.xml, oracle fp32 (C "
+                                   "sample": f"{cores} envs (one per host core) x 150 env steps, {args.model}.xml, oracle fp32 (C "
                                              "restatement of the MJX step; mujoco / mjx are not installable here)"}
         print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------ PPO train SPS
+def run_ppo(args):
+    """Second half of BASELINE.json's metric: PPO train SPS on the README configuration (configs[2] / [3]): 2048 envs per GPU,
+    unroll 10, batch 512 x 64 minibatches, 8 epochs, CG 8/8, normalised observations; `--steps` = training steps timed."""
+    import torch
+    import torch.distributed as dist
+    from brax_rodent_run_b200 import ppo
+    from brax_rodent_run_b200.env import Rodent
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the b200 arm has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = 2048 if args.envs == ENVS_PER_GPU else args.envs
+    env = Rodent(synthetic_track(), num_envs=B, device=dev, model=args.model, iterations=args.iterations,
+                 ls_iterations=args.ls_iterations, terminate_when_unhealthy=False, kinematics_outputs=False)
+    cfg = ppo.PPOConfig(num_envs=B)
+    agent = ppo.PPO(env.wrap_for_training(cfg.episode_length), cfg)
+    state = env.reset(rank)
+    for _ in range(max(1, min(args.warmup, 2))):
+        state, _ = agent.training_step(state)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    L = env._L
+    e0, l0, t0 = agent.env_steps, L.rr_launch_count(), time.perf_counter()
+    K = max(1, min(args.steps, 5))
+    for _ in range(K):
+        state, m = agent.training_step(state)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print(json.dumps({"metric": "PPO train SPS", "value": (agent.env_steps - e0) / float(dt.item()), "unit": "env-steps/s",
+                          "n_gpus": world, "steps": K, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": 1e3 * float(dt.item()) / K,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (TF32 matmuls in the MLPs)",
+                          "data": "synthetic",
+                          "config": {"workload": f"PPO on the {args.model}.xml run task, {B} envs/GPU, unroll 10, batch 512 x 64 "
+                                                 "minibatches, 8 epochs, normalised observations (readme.md:17-31)",
+                                     "iterations": args.iterations, "ls_iterations": args.ls_iterations,
+                                     "env_steps_per_training_step": (agent.env_steps - e0) // K},
+                          "gpu_launches": int(L.rr_launch_count() - l0),
+                          "losses": {k: float(v) for k, v in m.items()}}))
     if world > 1:
         dist.destroy_process_group()
 
@@ -325,11 +384,17 @@ def main():
     ap.add_argument("--iterations", type=int, default=8)      # brax_rodent_run_ppo.py:52
     ap.add_argument("--ls-iterations", type=int, default=8)   # brax_rodent_run_ppo.py:53
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--model", default="rodent_0", help="rodent_0 (BASELINE configs[1], default), rodent_pair (configs[4]), rodent_new, ...")
+    ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="environments per GPU")
+    ap.add_argument("--workload", default="step", choices=["step", "ppo"],
+                    help="step: env-steps/s of Rodent.step (the contract line, default); ppo: PPO train SPS")
     ap.add_argument("--balance", action="store_true",
                     help="cost-sorted env -> CTA assignment (off: measured slower than the even contiguous split, see DESIGN.md)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "ppo":
+        run_ppo(args)
     else:
         run_b200(args)
 

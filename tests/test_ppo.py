@@ -108,3 +108,51 @@ def test_two_rank_gloo_training_step(emu_lib):
     cfg_steps = TINY["batch_size"] * TINY["num_minibatches"] * TINY["unroll_length"]
     assert same_params and same_norm
     assert count == 2 * TINY["num_envs"] and env_steps == 2 * cfg_steps
+
+
+@pytest.mark.gpu
+def test_graphed_update_matches_eager_update():
+    """The CUDA-graph replay of the minibatch update (loss + backward + Adam) must report the same losses and apply the same
+    parameter update as the eager code on the same minibatch, entropy noise, parameters and Adam state."""
+    from brax_rodent_run_b200.env import Rodent
+    from brax_rodent_run_b200.ppo import PPO, PPOConfig
+    cfg = PPOConfig(num_envs=64, batch_size=16, num_minibatches=8, unroll_length=4, num_updates_per_batch=2, episode_length=50,
+                    num_timesteps=1, policy_hidden=(32, 32), value_hidden=(64, 64), tf32=False, cuda_graph=True)
+    env = Rodent(synthetic_track(), num_envs=64, device="cuda:0", model=load_asset("rodent_0"), iterations=4, ls_iterations=4,
+                 terminate_when_unhealthy=False).wrap_for_training(cfg.episode_length)
+    agent = PPO(env, cfg)
+    state = env.reset(0)
+    state, metrics = agent.training_step(state)          # warm-up updates, capture, replays
+    assert agent._graph is not None
+    assert all(math.isfinite(float(v)) for v in metrics.values())
+    chunks = []
+    for _ in range(cfg.batch_size * cfg.num_minibatches // cfg.num_envs):
+        state, d = agent.unroll(state)
+        chunks.append(d)
+    data = {k: torch.cat([c[k] for c in chunks], dim=1 if k != "next_observation_last" else 0) for k in chunks[0]}
+    idx = torch.arange(3, 3 + cfg.batch_size, device="cuda:0")
+    opt_tensors = [t for st in agent.opt.state.values() for t in st.values() if torch.is_tensor(t)]
+    saved = [t.clone() for t in agent.params + opt_tensors]
+    gen_state = agent.gen.get_state()
+
+    def restore():
+        with torch.no_grad():
+            for t, v in zip(agent.params + opt_tensors, saved):
+                t.copy_(v)
+        agent.gen.set_state(gen_state)
+
+    m_graph = {k: float(v) for k, v in agent._update_graphed(data, idx).items()}
+    d_graph = torch.cat([(p.detach() - v).reshape(-1) for p, v in zip(agent.params, saved)]).cpu()
+    restore()
+    st = agent._static                                    # still holds the gathered minibatch
+    st["entropy_noise"].normal_(generator=agent.gen)      # same generator state -> same noise
+    total, m = agent.loss(st)
+    agent.opt.zero_grad(set_to_none=False)
+    total.backward()
+    agent.opt.step()
+    m_eager = {k: float(v) for k, v in m.items()}
+    d_eager = torch.cat([(p.detach() - v).reshape(-1) for p, v in zip(agent.params, saved)]).cpu()
+    for k in m_eager:
+        assert abs(m_graph[k] - m_eager[k]) <= 1e-4 * max(1.0, abs(m_eager[k])), (k, m_graph[k], m_eager[k])
+    assert float(d_eager.abs().max()) > 0.1 * cfg.learning_rate     # the update moved something
+    assert float((d_graph - d_eager).abs().max()) < 0.05 * cfg.learning_rate, float((d_graph - d_eager).abs().max())
