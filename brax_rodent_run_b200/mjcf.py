@@ -21,7 +21,7 @@ import copy
 import dataclasses
 import math
 import xml.etree.ElementTree as ET
-from typing import Dict, List, Optional
+from typing import Dict, List, Optional, Tuple
 
 import numpy as np
 
@@ -356,8 +356,28 @@ def _replicate_referrers(section: Optional[ET.Element], renames, ref_attrs):
                 section.insert(idx + i, c)
 
 
-def load_xml(path: str) -> FlatModel:
-    """Parse + compile an MJCF file into a FlatModel."""
+def _rescale_subtree(node: ET.Element, position_factor: float, size_factor: float) -> None:
+    """dm_control.locomotion.walkers.rescale.rescale_subtree on the XML tree (preprocessing/mjx_preprocess.py:80-84):
+    every explicit `pos` under the body tree (bodies, geoms, joints, sites, cameras, inertials) is multiplied by
+    `position_factor`, every explicit `size` by `size_factor`, `fromto` about its scaled midpoint; defaults are untouched."""
+    fmt = lambda v: " ".join(repr(float(x)) for x in v)
+    for child in list(node):
+        a = child.attrib
+        if "fromto" in a:
+            ft = _vec(a["fromto"], 6)
+            mid, half = position_factor * 0.5 * (ft[3:] + ft[:3]), size_factor * 0.5 * (ft[3:] - ft[:3])
+            a["fromto"] = fmt(np.concatenate([mid - half, mid + half]))
+        if "pos" in a:
+            a["pos"] = fmt(position_factor * _vec(a["pos"]))
+        if "size" in a:
+            a["size"] = fmt(size_factor * _vec(a["size"]))
+        if child.tag in ("body", "worldbody"):
+            _rescale_subtree(child, position_factor, size_factor)
+
+
+def load_xml(path: str, rescale: Optional[Tuple[float, float]] = None) -> FlatModel:
+    """Parse + compile an MJCF file into a FlatModel.  `rescale=(position_factor, size_factor)` applies dm_control's
+    rescale_subtree to the body tree first (the reference's mocap preprocessing uses 0.9, 0.9)."""
     try:
         tree = ET.parse(path)
     except (ET.ParseError, OSError) as e:  # MuJoCo raises ValueError on bad XML / missing file
@@ -405,6 +425,8 @@ def load_xml(path: str) -> FlatModel:
     worldbody = root.find("worldbody")
     if worldbody is None:
         raise ValueError("XML Error: missing <worldbody>")
+    if rescale is not None:
+        _rescale_subtree(worldbody, float(rescale[0]), float(rescale[1]))
     renames = _expand_replicates(worldbody, eulerseq, angle_scale)
     _replicate_referrers(root.find("actuator"), renames, ("joint",))
     _replicate_referrers(root.find("sensor"), renames, ("site", "body", "joint"))

@@ -19,6 +19,7 @@ import math
 import time
 from typing import Callable, Dict, Optional
 
+import numpy as np
 import torch
 import torch.distributed as dist
 import torch.nn as nn
@@ -367,6 +368,31 @@ class PPO:
         norm = dict(count=float(n.count), mean=n.mean.cpu().numpy(), summed_variance=n.summed_variance.cpu().numpy(),
                     std=n.std.cpu().numpy())
         return norm, mlp(self.policy)
+
+
+    def import_brax_params(self, params) -> None:
+        """Load `(normalizer, policy)` as pickled by brax `model.save_params` (brax_rodent_run_ppo.py:204-206,
+        render_rollout.ipynb:117-118) or by `export_brax_params`: the normaliser may be a dict or any object with
+        count / mean / std (/ summed_variance); the policy a flax param tree {"params": {"hidden_i": {kernel, bias}}}."""
+        norm, pol = params[0], params[1]
+        get = (lambda k: norm.get(k)) if isinstance(norm, dict) else (lambda k: getattr(norm, k, None))
+        n = self.normalizer
+        as_t = lambda x: torch.as_tensor(np.asarray(x), dtype=torch.float32, device=self.device)
+        n.count = torch.as_tensor(float(np.asarray(get("count"))), dtype=torch.float64, device=self.device)
+        n.mean, n.std = as_t(get("mean")), as_t(get("std"))
+        sv = get("summed_variance")
+        n.summed_variance = as_t(sv) if sv is not None else (n.std ** 2) * float(n.count)
+        layers = pol["params"] if "params" in pol else pol
+        lin = [m for m in self.policy if isinstance(m, nn.Linear)]
+        if len(layers) != len(lin):
+            raise ValueError(f"policy has {len(lin)} layers, the parameters {len(layers)}")
+        with torch.no_grad():
+            for i, l in enumerate(lin):
+                w, b = as_t(layers[f"hidden_{i}"]["kernel"]).t(), as_t(layers[f"hidden_{i}"]["bias"])
+                if w.shape != l.weight.shape:
+                    raise ValueError(f"hidden_{i}: kernel {tuple(w.t().shape)} does not fit {tuple(l.weight.t().shape)}")
+                l.weight.copy_(w); l.bias.copy_(b)
+        self._graph, self._graph_warm = None, 0
 
 
 def train(environment: Rodent, cfg: PPOConfig, progress_fn: Callable[[int, Dict], None] = lambda *a: None,

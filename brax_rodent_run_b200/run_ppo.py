@@ -35,7 +35,7 @@ def load_track(path):
     if path and os.path.exists(path):
         with open(path, "rb") as f:
             clip = pickle.load(f)
-        pos = getattr(clip, "position", clip)
+        pos = clip["position"] if isinstance(clip, dict) else getattr(clip, "position", clip)  # preprocess.save_reference_clip
         return np.asarray(pos, np.float32).reshape(-1, 3)
     return np.stack([0.002 * np.arange(250), np.zeros(250), np.full(250, 0.055)], 1).astype(np.float32)
 

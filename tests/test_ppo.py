@@ -61,6 +61,13 @@ def test_training_step_runs_and_learns_shapes(emu_lib):
     assert pol["params"]["hidden_0"]["kernel"].shape == (env.observation_size, 8)
     sd = agent.state_dict()
     agent.load_state_dict(sd)
+    # brax (normalizer, policy) parameter exchange: export -> pickle -> import into a fresh agent reproduces the policy
+    import pickle
+    other = PPO(env, PPOConfig(**dict(TINY, seed=7)))
+    other.import_brax_params(pickle.loads(pickle.dumps(agent.export_brax_params())))
+    a1, _, _ = agent.act(state.obs, deterministic=True)
+    a2, _, _ = other.act(state.obs, deterministic=True)
+    assert torch.allclose(a1, a2, atol=1e-6)
     # 8 samples make a degenerate normaliser (std clipped at 1e-6, as in brax); the loss itself is checked without it
     cfg2 = PPOConfig(**dict(TINY, normalize_observations=False))
     agent2 = PPO(env, cfg2)
