@@ -1,0 +1,75 @@
+"""Size-independent properties of the batched step at BASELINE.json's full size (4096 envs on the GPU; a handful on the
+emulator): environments are independent, so results must be bit-identical under re-execution, under any permutation of the
+batch, under the explicit env -> warp-slot order of the load balancer, and across batch sizes (ragged last CTA, B = 1).
+These pin the launch geometry (persistent CTAs, contiguous split, padding passes, rendezvous) -- bugs there do not show in
+small-batch parity against the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import backend_params, load_asset, synthetic_track
+
+FIELDS = ("qpos", "qvel", "act", "qacc_warmstart")
+
+
+def rollout(env, sf, nq_, nv_, actions):
+    st = env.reset_from(torch.tensor(sf), torch.tensor(nq_), torch.tensor(nv_))
+    for a in actions:
+        st = env.step(st, torch.tensor(a))
+    out = {k: getattr(st.pipeline_state, k).cpu().numpy().copy() for k in FIELDS}
+    out.update(obs=st.obs.cpu().numpy().copy(), reward=st.reward.cpu().numpy().copy(), done=st.done.cpu().numpy().copy(),
+               cur_frame=st.info["cur_frame"].cpu().numpy().copy())
+    return out
+
+
+def inputs(m, B, T, seed):
+    rng = np.random.default_rng(seed)
+    sf = rng.integers(0, 100, B)
+    nq_, nv_ = rng.uniform(-.01, .01, (B, m.nq)), rng.uniform(-.01, .01, (B, m.nv))
+    nq_[:, 2] += rng.uniform(-0.02, 0.03, B)  # some start in contact, some airborne: different solver work per warp
+    acts = rng.uniform(-1, 1, (T, B, m.nu)).astype(np.float32)
+    return sf, nq_, nv_, acts
+
+
+@pytest.mark.parametrize("backend", backend_params())
+def test_rerun_permutation_and_batch_size_invariance(backend, make_env):
+    m, track = load_asset("rodent_0"), synthetic_track()
+    B, T = (5, 2) if backend == "emu" else (4096, 3)
+    kw = dict(model=m, iterations=4, ls_iterations=4, n_frames=2 if backend == "emu" else 10, terminate_when_unhealthy=True)
+    sf, nq_, nv_, acts = inputs(m, B, T, 5)
+    env = make_env(backend, track, num_envs=B, **kw).wrap_for_training(episode_length=1000)
+    ref = rollout(env, sf, nq_, nv_, acts)
+    assert np.isfinite(ref["obs"]).all()
+    np.testing.assert_allclose(np.linalg.norm(ref["qpos"][:, 3:7], axis=1), 1.0, atol=2e-6)
+    # 1. re-execution
+    again = rollout(env, sf, nq_, nv_, acts)
+    for k in ref:
+        assert np.array_equal(ref[k], again[k]), k
+    # 2. permutation of the batch
+    perm = np.random.default_rng(9).permutation(B)
+    p = rollout(env, sf[perm], nq_[perm], nv_[perm], acts[:, perm])
+    for k in ref:
+        assert np.array_equal(ref[k][perm], p[k]), k
+    # 3. a smaller, ragged batch (and a single environment) reproduces the same environments
+    for Bs in ((3, 1) if backend == "emu" else (1481, 37, 1)):
+        small = make_env(backend, track, num_envs=Bs, **kw).wrap_for_training(episode_length=1000)
+        s = rollout(small, sf[:Bs], nq_[:Bs], nv_[:Bs], acts[:, :Bs])
+        for k in ref:
+            assert np.array_equal(ref[k][:Bs], s[k]), (Bs, k)
+
+
+@pytest.mark.gpu
+def test_balanced_order_is_bitwise_neutral():
+    """Rodent(balance=True) regroups environments over CTAs by last step's solver work; results must not depend on it."""
+    from brax_rodent_run_b200.env import Rodent
+    m, track = load_asset("rodent_0"), synthetic_track()
+    B, T = 4096, 3
+    sf, nq_, nv_, acts = inputs(m, B, T, 6)
+    outs = []
+    for balance in (False, True):
+        env = Rodent(track, num_envs=B, device="cuda:0", model=m, iterations=4, ls_iterations=4, balance=balance,
+                     terminate_when_unhealthy=True).wrap_for_training(episode_length=1000)
+        assert env._balance == balance
+        outs.append(rollout(env, sf, nq_, nv_, acts))
+    for k in outs[0]:
+        assert np.array_equal(outs[0][k], outs[1][k]), k
