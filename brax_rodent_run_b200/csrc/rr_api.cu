@@ -34,8 +34,14 @@
 
 /* Persistent CTAs: the model tables (about 29 KB for rodent_0) are staged into shared memory once per CTA, then each
  * warp loops over its share of the environments. */
+/* Models with more than 96 dofs (NS = 5 register slots per nv-vector, e.g. rodent_pair) need > 168 registers per thread and
+ * at most 5 of their 40 KB environments fit an SM anyway: bound that instantiation at 6 warps so that nothing spills
+ * (spilled, it ran 1.9x slower: local memory competes for the ~28 KB of L1 left beside the 227 KB of shared memory). */
+#define RR_MAX_WPB_WIDE 6
+template <int NS> struct RRMaxWpb { static constexpr int value = NS <= 3 ? RR_MAX_WPB : (RR_MAX_WPB < RR_MAX_WPB_WIDE ? RR_MAX_WPB : RR_MAX_WPB_WIDE); };
+
 template <int NS, bool DBG>
-__global__ void __launch_bounds__(32 * RR_MAX_WPB, 1) rr_step_kernel(const __grid_constant__ RRModelDev m,
+__global__ void __launch_bounds__(32 * RRMaxWpb<NS>::value, 1) rr_step_kernel(const __grid_constant__ RRModelDev m,
                                                                      const __grid_constant__ RRStepArgs a) {
   extern __shared__ float4 rr_smem4[];
   int32_t *ti = reinterpret_cast<int32_t *>(rr_smem4);
@@ -114,6 +120,8 @@ static int rrb_num_slots() {
 }
 static int rrb_sync(void *stream) { return rrb_check(cudaStreamSynchronize((cudaStream_t)stream), "cudaStreamSynchronize"); }
 
+static int rrb_max_wpb(const RRModelDev &m) { return m.nv <= 96 ? RRMaxWpb<3>::value : RRMaxWpb<5>::value; }
+
 static int rrb_geometry(const RRModelDev &m, int B, int *ctas, int *wpb_out) {
   const size_t tables = ((size_t)m.ni + m.nf) * 4, per_env = (size_t)m.sm.total * sizeof(float);
   if (tables + per_env > RR_SMEM_MAX) {
@@ -122,7 +130,7 @@ static int rrb_geometry(const RRModelDev &m, int B, int *ctas, int *wpb_out) {
     return 1;
   }
   int wpb = (int)((RR_SMEM_MAX - tables) / per_env);
-  if (wpb > RR_MAX_WPB) wpb = RR_MAX_WPB;
+  if (wpb > rrb_max_wpb(m)) wpb = rrb_max_wpb(m);
   if (const char *ov = getenv("RR_WPB")) { /* developer knob: fewer environments per CTA (occupancy experiments) */
     int v = atoi(ov);
     if (v >= 1 && v < wpb) wpb = v;
