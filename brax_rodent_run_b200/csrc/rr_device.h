@@ -16,7 +16,7 @@
 #define RR_DEV_INT_TABLES(X)                                                                              \
   X(body_parentid) X(body_eparent) X(body_rootslot) X(body_jntadr) X(body_jntnum) X(level_adr) X(level_body)              \
   X(jnt_type) X(jnt_qposadr) X(jnt_dofadr) X(jnt_bodyid)                                                  \
-  X(dof_bodyid) X(dof_depth) X(dof_ndesc) X(dof_rowadr) X(dof_log2w) X(dof_pack) X(dof_cbmask) X(M_meta)                            \
+  X(dof_bodyid) X(dof_depth) X(dof_ndesc) X(dof_rowadr) X(dof_log2w) X(dof_pack) X(dof_cbmask) X(dof_descmask) X(dof_ancmask) X(M_meta)                            \
   X(act_dofadr) X(act_qposadr) X(act_dyntype) X(act_gaintype) X(act_biastype) X(act_ctrllimited)          \
   X(act_forcelimited) X(act_actadr)                                                                       \
   X(pair_fn) X(pair_body) X(pair_conadr) X(pair_lastdof) X(pair_cb) X(cb_lastdof) X(cb_conadr) X(cb_conlist) X(con_pair)                          \
@@ -56,10 +56,10 @@ struct RRModelDev {
   RRSmem sm;
   /* The tables live in two contiguous device buffers; the kernel stages both into shared memory once per CTA and
    * indexes them through the element offsets o_<table> below (RI / RF macros in rr_kernels.inl). */
-  /* Per-dof layout word (rowadr | depth << 16 | ndesc << 24) by value: the struct is a __grid_constant__ kernel
-   * parameter, so kdof_pack[i] with a warp-uniform i is a constant-bank load into a uniform register -- the solve loops
-   * index it once per column without touching the LSU or vector registers.  Zero beyond nv (columns that do nothing). */
-  int32_t kdof_pack[160];
+  /* Per-dof layout by value: the struct is a __grid_constant__ kernel parameter, so k*[i] with a warp-uniform i is a
+   * constant-bank load -- the solve loops index these once per column without touching the LSU.  Byte offsets (x 4) so that
+   * a coefficient address is one add: krow4[i] = 4 rowadr[i], kdep4[i] = 4 depth[i].  Zero beyond nv. */
+  int32_t krow4[160], kdep4[160];
   const int32_t *ibuf;
   const float *fbuf;
   int ni, nf; /* element counts of ibuf / fbuf (multiples of 4) */

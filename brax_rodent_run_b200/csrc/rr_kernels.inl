@@ -67,6 +67,22 @@
 #define RR_PRAGMA_(x) _Pragma(#x)
 #define RR_UNROLL(n) RR_PRAGMA_(unroll n)
 
+/* Raw shared-memory addressing for the solve loops: a 32-bit shared-window byte address per lane plus a byte offset is
+ * ONE integer add in front of the load (generic C++ indexing costs an add and a shift-add).  The host emulator provides
+ * plain-pointer versions. */
+#ifndef RR_SADDR_T
+#define RR_SADDR_T unsigned
+#define RR_SADDR(p) ((unsigned)__cvta_generic_to_shared(p))
+__device__ __forceinline__ float rr_lds_f32(unsigned a) {
+  float v;
+  asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+#define RR_SLOAD(a) rr_lds_f32(a)
+/* (an inline-PTX predicated load + in-place predicated FMA was tried for this update: ptxas then spills 4 KB) */
+#define RR_SOLVE_UPDATE(x, m, bit, a, xi) do { if ((m) & (bit)) (x) -= RR_SLOAD(a) * (xi); } while (0)
+#endif
+
 #define RR_FULL 0xffffffffu
 #define RR_MINVAL 1e-15f
 #define RR_MINIMP 0.0001f
@@ -663,47 +679,72 @@ RR_DEV void factor2(Ctx<NS> &c, float dt) {
   __syncwarp();
 }
 
-/* One dof per step in index order, per-slot loops so that the broadcast register is a compile-time choice, no branch in
- * the body and all metadata / coefficient loads independent of x: the only dependent chain left is shuffle -> FMA
- * (-> next shuffle).  The per-column layout word comes from the constant bank (kdof_pack) into uniform registers, the
- * coefficient address is a per-lane pointer plus that uniform offset, and slots other than the last run a fixed 32
- * columns (columns beyond nv have an all-zero layout word and update nothing), so a column costs the shuffle plus
- * compare / predicated load / predicated FMA per slot. */
+/* One dof (column) per step in index order, in groups of 8 columns; per-slot code so that the broadcast register is a
+ * compile-time choice, no branch in the body and all metadata / coefficient loads independent of x: the only dependent chain
+ * is shuffle -> FMA (-> next shuffle).  Per column and slot the work is: test one bit of a static mask (is this column a
+ * descendant / an ancestor of my dof -- host tables dof_descmask / dof_ancmask, shifted once per group), one add for the
+ * coefficient address (per-lane shared-memory byte address + the column's byte offset from the constant bank), the load
+ * and the FMA.  Columns beyond nv have empty masks and do nothing (the last slot runs whole groups of 8). */
 template <int NS>
 RR_DEV void solve_ld(Ctx<NS> &c, float (&x)[NS], const float *LDm, const float (&dinv)[NS]) {
   const int nv = c.m.nv;
-  const float *lcol[NS], *lrow[NS]; /* &L(., lane dof) within a row; row of the lane dof */
-  unsigned nj[NS];                  /* -1 - lane dof: (i - 1 - j) = i + nj */
-  RR_FOR_S { lcol[s] = LDm + c.dep[s]; lrow[s] = LDm + c.radr[s]; nj[s] = (unsigned)(-1 - (c.lane + 32 * s)); }
-  /* backward: x <- L^-T x, leaves to root; dof i updates its ancestors j: (unsigned)(i - j - 1) < ndesc[j] */
+  const int nb32 = (nv + 31) >> 5;
+  RR_SADDR_T lcol[NS], lrow[NS]; /* byte address of L(., lane dof) in row 0; of the row of the lane dof */
+  RR_FOR_S { lcol[s] = RR_SADDR(LDm + c.dep[s]); lrow[s] = RR_SADDR(LDm + c.radr[s]); }
+  /* backward: x <- L^-T x, leaves to root; column i updates its ancestors = the dofs that have i as a descendant */
 #pragma unroll
   for (int si = NS - 1; si >= 0; si--) {
-    const int top = si == NS - 1 ? ((nv - 32 * si) < 32 ? (nv - 32 * si) : 32) : 32;
-RR_UNROLL(RR_SOLVE_UNROLL)
-    for (int src = top - 1; src >= 0; src--) {
-      const int i = 32 * si + src;
-      const int adr = c.m.kdof_pack[i] & 0xffff;
-      const float xi = __shfl_sync(RR_FULL, x[si], src);
+    if (32 * si >= nv) continue;
+    unsigned dm[NS];
 #pragma unroll
-      for (int s = 0; s <= si; s++) {
-        if ((unsigned)i + nj[s] < (unsigned)c.nd[s]) x[s] -= lcol[s][adr] * xi;
+    for (int s = 0; s <= si; s++) {
+      const int j = c.lane + 32 * s;
+      dm[s] = j < nv ? (unsigned)RI(dof_descmask, j * nb32 + si) : 0u;
+    }
+    const int ng = si == NS - 1 ? (((nv - 32 * si) < 32 ? (nv - 32 * si) : 32) + 7) >> 3 : 4;
+#pragma unroll 1
+    for (int g = ng - 1; g >= 0; g--) {
+      unsigned mg[NS];
+#pragma unroll
+      for (int s = 0; s <= si; s++) mg[s] = dm[s] >> (8 * g);
+#pragma unroll
+      for (int k = 7; k >= 0; k--) {
+        const int src = 8 * g + k;
+        const int adr4 = c.m.krow4[32 * si + src];
+        const float xi = __shfl_sync(RR_FULL, x[si], src);
+#pragma unroll
+        for (int s = 0; s <= si; s++) {
+          RR_SOLVE_UPDATE(x[s], mg[s], 1u << k, lcol[s] + adr4, xi);
+        }
       }
     }
   }
   RR_FOR_S x[s] *= dinv[s];
-  /* forward: x <- L^-1 x, root to leaves; dof j updates its descendants i: (unsigned)(i - j - 1) < ndesc[j] */
+  /* forward: x <- L^-1 x, root to leaves; column j updates its descendants = the dofs that have j as an ancestor */
 #pragma unroll
   for (int sj = 0; sj < NS; sj++) {
-    const int top = sj == NS - 1 ? ((nv - 32 * sj) < 32 ? (nv - 32 * sj) : 32) : 32;
-RR_UNROLL(RR_SOLVE_UNROLL)
-    for (int src = 0; src < top; src++) {
-      const int j = 32 * sj + src;
-      const unsigned pk = (unsigned)c.m.kdof_pack[j]; /* rowadr | depth << 16 | ndesc << 24 */
-      const unsigned ndj = pk >> 24, dpj = (pk >> 16) & 255;
-      const float xj = __shfl_sync(RR_FULL, x[sj], src);
+    if (32 * sj >= nv) continue;
+    unsigned am[NS];
 #pragma unroll
-      for (int s = sj; s < NS; s++) {
-        if ((unsigned)(c.lane + 32 * s - 1 - j) < ndj) x[s] -= lrow[s][dpj] * xj;
+    for (int s = sj; s < NS; s++) {
+      const int i = c.lane + 32 * s;
+      am[s] = i < nv ? (unsigned)RI(dof_ancmask, i * nb32 + sj) : 0u;
+    }
+    const int ng = sj == NS - 1 ? (((nv - 32 * sj) < 32 ? (nv - 32 * sj) : 32) + 7) >> 3 : 4;
+#pragma unroll 1
+    for (int g = 0; g < ng; g++) {
+      unsigned mg[NS];
+#pragma unroll
+      for (int s = sj; s < NS; s++) mg[s] = am[s] >> (8 * g);
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const int src = 8 * g + k;
+        const int dp4 = c.m.kdep4[32 * sj + src];
+        const float xj = __shfl_sync(RR_FULL, x[sj], src);
+#pragma unroll
+        for (int s = sj; s < NS; s++) {
+          RR_SOLVE_UPDATE(x[s], mg[s], 1u << k, lrow[s] + dp4, xj);
+        }
       }
     }
   }

@@ -194,7 +194,18 @@ inline void rr_host_model_build(RRHostModel &hm, const int32_t *dir, const int32
   /* packed dof metadata: rowadr | depth << 16 | ndesc << 24 */
   t_dof_pack.resize(nv);
   for (int i = 0; i < nv; i++) t_dof_pack[i] = t_dof_rowadr[i] | (t_dof_depth[i] << 16) | (t_dof_ndesc[i] << 24);
-  for (int i = 0; i < 160; i++) d.kdof_pack[i] = i < nv ? t_dof_pack[i] : 0;
+  for (int i = 0; i < 160; i++) { d.krow4[i] = i < nv ? 4 * t_dof_rowadr[i] : 0; d.kdep4[i] = i < nv ? 4 * t_dof_depth[i] : 0; }
+  /* per dof and block of 32 columns: which columns are descendants / ancestors of the dof (the solves' predicates) */
+  {
+    const int nb32 = (nv + 31) / 32;
+    t_dof_descmask.assign((size_t)std::max(nv, 1) * std::max(nb32, 1), 0);
+    t_dof_ancmask.assign((size_t)std::max(nv, 1) * std::max(nb32, 1), 0);
+    for (int j = 0; j < nv; j++)
+      for (int i = j + 1; i <= j + t_dof_ndesc[j]; i++) {
+        t_dof_descmask[(size_t)j * nb32 + i / 32] |= (int32_t)(1u << (i & 31));
+        t_dof_ancmask[(size_t)i * nb32 + j / 32] |= (int32_t)(1u << (j & 31));
+      }
+  }
   if (t_dof_pack.empty()) t_dof_pack.push_back(0);
   /* factor(): row width rounded up to a power of two (log2), for the lane-group split of short rows */
   t_dof_log2w.assign(nv, 5);

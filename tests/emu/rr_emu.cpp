@@ -117,6 +117,11 @@ static inline int __float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; 
 #define RR_LDG(p) (*(p))
 #define RR_CLOCK() 0LL
 #define RR_CTA_SYNC() ((void)0)
+typedef const char *rr_emu_saddr;
+#define RR_SADDR_T rr_emu_saddr
+#define RR_SADDR(p) ((rr_emu_saddr)(p))
+#define RR_SLOAD(a) (*(const float *)(a))
+#define RR_SOLVE_UPDATE(x, m, bit, a, xi) do { if ((m) & (bit)) (x) -= RR_SLOAD(a) * (xi); } while (0)
 
 #include "../../brax_rodent_run_b200/csrc/rr_kernels.inl"
 
