@@ -89,6 +89,18 @@ __device__ __forceinline__ float rr_lds_f32(unsigned a) {
 #define RR_MAXIMP 0.9999f
 #define RR_SIGN_BIT 0x40000000
 
+/* Reciprocal on the critical paths (pivot of a factorisation row, Newton steps of the line search): the IEEE division is
+ * a 7-instruction sequence with a branch to a slow path (ptxas cannot schedule across it); MUFU.RCP plus one Newton step is
+ * 3 straight-line instructions and accurate to about 1 ulp for the normal, positive arguments met here. */
+#ifndef RR_RCP
+__device__ __forceinline__ float rr_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return fmaf(r, fmaf(-x, r, 1.f), r);
+}
+#define RR_RCP(x) rr_rcp(x)
+#endif
+
 namespace RR_NS {
 
 RR_DEV float warp_sum(float x) {
@@ -136,13 +148,15 @@ RR_DEV void axis_angle_quat(float *q, const float *axis, float angle) {
 RR_DEV float normalize3(float *v) {
   float n = sqrtf(dot3(v, v));
   float d = n + 1e-6f * (n == 0.f ? 1.f : 0.f);
-  v[0] /= d; v[1] /= d; v[2] /= d;
+  const float id = RR_RCP(d);
+  v[0] *= id; v[1] *= id; v[2] *= id;
   return n;
 }
 RR_DEV void normalize4(float *v) {
   float n = sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2] + v[3] * v[3]);
   float d = n + 1e-6f * (n == 0.f ? 1.f : 0.f);
-  v[0] /= d; v[1] /= d; v[2] /= d; v[3] /= d;
+  const float id = RR_RCP(d);
+  v[0] *= id; v[1] *= id; v[2] *= id; v[3] *= id;
 }
 /* mjx math.inert_mul: cinert(10) x motion(6: ang, lin) -> force(6) */
 RR_DEV void inert_mul(float *r, const float *i, const float *v) {
@@ -179,13 +193,19 @@ RR_DEV_NOINLINE void kbi(float timestep, const float *solref, const float *solim
   float timeconst = fmaxf(solref[0], 2.f * timestep), dampratio = solref[1];
   float dmin = clampf(solimp[0], RR_MINIMP, RR_MAXIMP), dmax = clampf(solimp[1], RR_MINIMP, RR_MAXIMP);
   float width = fmaxf(solimp[2], RR_MINVAL), mid = clampf(solimp[3], RR_MINIMP, RR_MAXIMP), power = fmaxf(solimp[4], 1.f);
-  k = 1.f / (dmax * dmax * timeconst * timeconst * dampratio * dampratio);
-  b = 2.f / (dmax * timeconst);
+  k = RR_RCP(dmax * dmax * timeconst * timeconst * dampratio * dampratio);
+  b = 2.f * RR_RCP(dmax * timeconst);
   if (solref[0] <= 0.f) k = -solref[0] / (dmax * dmax);
   if (solref[1] <= 0.f) b = -solref[1] / dmax;
-  float x = fabsf(pos) / width;
-  float ia = (1.f / powf(mid, power - 1.f)) * powf(x, power);
-  float ib = 1.f - (1.f / powf(1.f - mid, power - 1.f)) * powf(1.f - x, power);
+  float x = fabsf(pos) * RR_RCP(width);
+  float ia, ib;
+  if (power == 2.f) { /* the MuJoCo default (every rodent model): no powf */
+    ia = RR_RCP(mid) * (x * x);
+    ib = 1.f - RR_RCP(1.f - mid) * ((1.f - x) * (1.f - x));
+  } else {
+    ia = (1.f / powf(mid, power - 1.f)) * powf(x, power);
+    ib = 1.f - (1.f / powf(1.f - mid, power - 1.f)) * powf(1.f - x, power);
+  }
   float y = x < mid ? ia : ib;
   float im = clampf(dmin + y * (dmax - dmin), dmin, dmax);
   imp = x > 1.f ? dmax : im;
@@ -433,9 +453,10 @@ RR_DEV void com_pos(Ctx<NS> &c) {
     sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz); sm = warp_sum(sm);
     if (c.lane == 0) {
       bool tiny = sm < RR_MINVAL;
-      c.com[3 * r + 0] = tiny ? 0.f : sx / sm;
-      c.com[3 * r + 1] = tiny ? 0.f : sy / sm;
-      c.com[3 * r + 2] = tiny ? 0.f : sz / sm;
+      const float ism = RR_RCP(tiny ? 1.f : sm);
+      c.com[3 * r + 0] = tiny ? 0.f : sx * ism;
+      c.com[3 * r + 1] = tiny ? 0.f : sy * ism;
+      c.com[3 * r + 2] = tiny ? 0.f : sz * ism;
     }
   }
   __syncwarp();
@@ -595,12 +616,12 @@ RR_DEV void factor2(Ctx<NS> &c, float dt) {
       /* finish row k, fold it into row k - 1, finish row k - 1 */
       const float dA1 = __shfl_sync(RR_FULL, a1, mk), dA2 = __shfl_sync(RR_FULL, a2, mk);
       const float wk1 = __shfl_sync(RR_FULL, a1, mk - 1), wk2 = __shfl_sync(RR_FULL, a2, mk - 1); /* L(k, k-1) D_k */
-      const float iA1 = 1.f / dA1, iA2 = 1.f / dA2;
+      const float iA1 = RR_RCP(dA1), iA2 = RR_RCP(dA2);
       const float lA1 = a1 * iA1, lA2 = a2 * iA2;
       b1 -= onB ? wk1 * lA1 : 0.f;
       b2 -= onB ? wk2 * lA2 : 0.f;
       const float dB1 = __shfl_sync(RR_FULL, b1, mk - 1), dB2 = __shfl_sync(RR_FULL, b2, mk - 1);
-      const float iB1 = 1.f / dB1, iB2 = 1.f / dB2;
+      const float iB1 = RR_RCP(dB1), iB2 = RR_RCP(dB2);
       if (g == 0 && s0 < mk) { LD[adr + s0] = lA1; L2[adr + s0] = lA2; }
       if (g == 0 && s0 < mk - 1) { LD[adrp + s0] = b1 * iB1; L2[adrp + s0] = b2 * iB2; }
       if (c.lane == 0) { LD[adr + mk] = dA1; L2[adr + mk] = dA2; LD[adrp + mk - 1] = dB1; L2[adrp + mk - 1] = dB2; }
@@ -636,7 +657,7 @@ RR_DEV void factor2(Ctx<NS> &c, float dt) {
         acc2 += __shfl_xor_sync(RR_FULL, acc2, o);
       }
       const float dk = __shfl_sync(RR_FULL, acc, mk), dk2 = __shfl_sync(RR_FULL, acc2, mk);
-      const float inv = 1.f / dk, inv2 = 1.f / dk2;
+      const float inv = RR_RCP(dk), inv2 = RR_RCP(dk2);
       if (g == 0 && s0 < mk) { LD[adr + s0] = acc * inv; L2[adr + s0] = acc2 * inv2; }
       if (c.lane == 0) { LD[adr + mk] = dk; L2[adr + mk] = dk2; }
     } else {
@@ -657,7 +678,7 @@ RR_DEV void factor2(Ctx<NS> &c, float dt) {
         b1 -= on1 ? wr.y * L2[rj + so1] : 0.f;
       }
       const float dk = __shfl_sync(RR_FULL, a1, mk & 31), dk2 = __shfl_sync(RR_FULL, b1, mk & 31);
-      const float inv = 1.f / dk, inv2 = 1.f / dk2;
+      const float inv = RR_RCP(dk), inv2 = RR_RCP(dk2);
       LD[adr + s0] = a0 * inv; L2[adr + s0] = b0 * inv2;
       if (s1 < mk) { LD[adr + s1] = a1 * inv; L2[adr + s1] = b1 * inv2; }
       if (c.lane == 0) { LD[adr + mk] = dk; L2[adr + mk] = dk2; }
@@ -671,7 +692,7 @@ RR_DEV void factor2(Ctx<NS> &c, float dt) {
     float d1 = 0.f, d2 = 0.f;
     if (i < m.nv) {
       const int e = c.radr[s] + c.dep[s];
-      d1 = 1.f / LD[e]; d2 = 1.f / L2[e];
+      d1 = RR_RCP(LD[e]); d2 = RR_RCP(L2[e]);
       LD[e] = d1; L2[e] = d2;
     }
     c.dinv[s] = d1; c.dinv2[s] = d2;
@@ -888,7 +909,7 @@ RR_DEV void smooth_forces(Ctx<NS> &c, const float (&qfrc_bias)[NS]) {
     if (RI(act_dyntype, u) == 2) {
       int aa = RI(act_actadr, u);
       float tau = fmaxf(RF(act_dynprm, u), RR_MINVAL);
-      c.actdot[aa] = (ctrl - c.act[aa]) / tau;
+      c.actdot[aa] = (ctrl - c.act[aa]) * RR_RCP(tau);
       ctrl_act = c.act[aa];
     }
     float gain = RF(act_gainprm, 3 * u);
@@ -1173,9 +1194,9 @@ RR_DEV void make_constraint(Ctx<NS> &c) {
 #pragma unroll
       for (int q = 0; q < 5; q++) si[q] = RF(limit_solimp, 5 * l + q);
       kbi(m.timestep, sr, si, pos, k, b, imp);
-      float R = fmaxf(RF(limit_invweight, l) * (1.f - imp) / imp, RR_MINVAL);
+      float R = fmaxf(RF(limit_invweight, l) * (1.f - imp) * RR_RCP(imp), RR_MINVAL);
       c.row_id[r] = l | (dlo < dhi ? 0 : RR_SIGN_BIT);
-      c.row_D[r] = 1.f / R;
+      c.row_D[r] = RR_RCP(R);
       c.row_aref[r] = k * imp * pos; /* temp: completed below */
       c.row_Jaref[r] = b;            /* temp */
     }
@@ -1206,12 +1227,12 @@ RR_DEV void make_constraint(Ctx<NS> &c) {
     kbi(m.timestep, sr, si, pos, kk, b, imp);
     float mu = RF(pair_mu, p), t = RF(pair_invweight, p);
     float invw = (t + mu * mu * t) * 2.f * mu * mu / m.impratio;
-    float R = fmaxf(invw * (1.f - imp) / imp, RR_MINVAL);
+    float R = fmaxf(invw * (1.f - imp) * RR_RCP(imp), RR_MINVAL);
 #pragma unroll
     for (int q = 0; q < 4; q++) {
       int r = nla + 4 * k + q;
       c.row_id[r] = m.nlimit + 4 * cc + q;
-      c.row_D[r] = 1.f / R;
+      c.row_D[r] = RR_RCP(R);
       c.row_aref[r] = kk * imp * pos;
       c.row_Jaref[r] = b;
     }
@@ -1419,7 +1440,7 @@ RR_DEV void solve_constraints(Ctx<NS> &c) {
         LSPoint r1[1];
         for (int pass = 0; pass < 2; pass++) {
           ls_eval<NS, 1>(c, nra, a1, g0, g1, g2, r1);
-          if (pass == 0) { p0 = r1[0]; a1[0] = p0.alpha - p0.d0 / p0.d1; }
+          if (pass == 0) { p0 = r1[0]; a1[0] = p0.alpha - p0.d0 * RR_RCP(p0.d1); }
         }
         lo = r1[0];
       }
@@ -1432,7 +1453,7 @@ RR_DEV void solve_constraints(Ctx<NS> &c) {
         done |= (lo.d0 < 0.f) && (lo.d0 > -gtol);
         done |= (hi.d0 > 0.f) && (hi.d0 < gtol);
         if (done) break;
-        float a3[3] = {lo.alpha - lo.d0 / lo.d1, hi.alpha - hi.d0 / hi.d1, 0.5f * (lo.alpha + hi.alpha)};
+        float a3[3] = {lo.alpha - lo.d0 * RR_RCP(lo.d1), hi.alpha - hi.d0 * RR_RCP(hi.d1), 0.5f * (lo.alpha + hi.alpha)};
         LSPoint r3[3];
         ls_eval<NS, 3>(c, nra, a3, g0, g1, g2, r3);
         LSPoint lo_next = r3[0], hi_next = r3[1], mid = r3[2];
@@ -1479,7 +1500,7 @@ RR_DEV void solve_constraints(Ctx<NS> &c) {
         num += __shfl_xor_sync(RR_FULL, num, o);
         den += __shfl_xor_sync(RR_FULL, den, o);
       }
-      beta = fmaxf(0.f, num / fmaxf(RR_MINVAL, den));
+      beta = fmaxf(0.f, num * RR_RCP(fmaxf(RR_MINVAL, den)));
       RR_FOR_S search[s] = -Mgrad[s] + beta * search[s];
       niter++;
     }

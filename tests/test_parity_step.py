@@ -239,7 +239,7 @@ def test_trajectory_statistics(backend, make_env, oracle_mod):
     the return and the health statistics -- with the oracle's, and hold the early part of the trajectory to the
     fp32-vs-fp64 yardstick."""
     m, track = load_asset("rodent_0"), synthetic_track()
-    B = 2 if backend == "emu" else 16
+    B = 2 if backend == "emu" else 48
     T = 6 if backend == "emu" else 100
     kw = dict(iterations=4, ls_iterations=4, terminate_when_unhealthy=False)
     env = make_env(backend, track, num_envs=B, model=m, **kw)
@@ -265,7 +265,10 @@ def test_trajectory_statistics(backend, make_env, oracle_mod):
         z_o.append(np.array([oe.o.get("qpos")[2] for oe in oes]))
         assert torch.isfinite(st.obs).all()
     z_k, z_o = np.array(z_k), np.array(z_o)
-    # the quadctrl part of the return is identical; tracking + alive parts agree in the mean over envs and time
-    assert abs(ret_k.mean() - ret_o.mean()) < 0.05 * T
+    # the quadctrl part of the return is identical; tracking + alive parts agree in the mean over envs and time.  Per-env
+    # returns of the two (chaotic) rollouts decorrelate, so the bound on the difference of the means is 4 standard errors
+    # of that difference (plus the old 5 % of T floor for the tiny emulator batch)
+    se = np.sqrt((ret_k.var() + ret_o.var()) / B)
+    assert abs(ret_k.mean() - ret_o.mean()) < max(4.0 * se, 0.05 * T), (ret_k.mean(), ret_o.mean(), se)
     assert abs(z_k.mean() - z_o.mean()) < 0.02
     assert z_k.min() > -0.2 and z_k.max() < 1.0  # nothing blew up
