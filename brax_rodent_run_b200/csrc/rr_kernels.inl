@@ -99,6 +99,33 @@ __device__ __forceinline__ float rr_rcp(float x) {
   return fmaf(r, fmaf(-x, r, 1.f), r);
 }
 #define RR_RCP(x) rr_rcp(x)
+/* sqrt without the IEEE fix-up / slow path (1 ulp) */
+__device__ __forceinline__ float rr_sqrt(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+#define RR_SQRT(x) rr_sqrt(x)
+/* sin and cos of a joint half-angle: quadrant reduction (two-constant Cody-Waite, exact enough far beyond any joint range)
+ * and the classic single-precision minimax polynomials on [-pi/4, pi/4] (about 1 ulp), straight-line -- libdevice's
+ * sincosf carries a branch to a Payne-Hanek slow path inside the serial tree walk of the kinematics */
+__device__ __forceinline__ void rr_sincos(float x, float *sn, float *cs) {
+  const float q = rintf(x * 0.636619772367581343f);
+  float r = fmaf(q, -1.5707962512969971f, x);
+  r = fmaf(q, -7.5497894158615964e-8f, r);
+  const float r2 = r * r;
+  float ps = fmaf(r2, -1.9515295891e-4f, 8.3321608736e-3f);
+  ps = fmaf(ps, r2, -1.6666654611e-1f);
+  ps = fmaf(ps * r2, r, r);
+  float pc = fmaf(r2, 2.443315711809948e-5f, -1.388731625493765e-3f);
+  pc = fmaf(pc, r2, 4.166664568298827e-2f);
+  pc = fmaf(pc * r2, r2, fmaf(r2, -0.5f, 1.f));
+  const int k = (int)q;
+  const float s0 = (k & 1) ? pc : ps, c0 = (k & 1) ? ps : pc;
+  *sn = (k & 2) ? -s0 : s0;
+  *cs = ((k + 1) & 2) ? -c0 : c0;
+}
+#define RR_SINCOS(x, s, c) rr_sincos(x, s, c)
 #endif
 
 namespace RR_NS {
@@ -142,18 +169,18 @@ RR_DEV void quat_to_mat(float *m, const float *q) {
 }
 RR_DEV void axis_angle_quat(float *q, const float *axis, float angle) {
   float s, c;
-  sincosf(angle * 0.5f, &s, &c);
+  RR_SINCOS(angle * 0.5f, &s, &c);
   q[0] = c; q[1] = axis[0] * s; q[2] = axis[1] * s; q[3] = axis[2] * s;
 }
 RR_DEV float normalize3(float *v) {
-  float n = sqrtf(dot3(v, v));
+  float n = RR_SQRT(dot3(v, v));
   float d = n + 1e-6f * (n == 0.f ? 1.f : 0.f);
   const float id = RR_RCP(d);
   v[0] *= id; v[1] *= id; v[2] *= id;
   return n;
 }
 RR_DEV void normalize4(float *v) {
-  float n = sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2] + v[3] * v[3]);
+  float n = RR_SQRT(v[0] * v[0] + v[1] * v[1] + v[2] * v[2] + v[3] * v[3]);
   float d = n + 1e-6f * (n == 0.f ? 1.f : 0.f);
   const float id = RR_RCP(d);
   v[0] *= id; v[1] *= id; v[2] *= id; v[3] *= id;
@@ -1405,7 +1432,7 @@ RR_DEV void solve_constraints(Ctx<NS> &c) {
     if (!finished && !first) {
       if (m.iterations != 1) {
         float improvement = (prev_cost - cost) * scale;
-        float gradient = sqrtf(vdot<NS>(grad, grad)) * scale;
+        float gradient = RR_SQRT(vdot<NS>(grad, grad)) * scale;
         if (niter >= m.iterations || improvement < m.tolerance || gradient < m.tolerance) finished = true;
       } else if (niter >= 1) {
         finished = true;
@@ -1413,7 +1440,7 @@ RR_DEV void solve_constraints(Ctx<NS> &c) {
     }
     if (!finished && !first) {
       /* ---- linesearch ---- */
-      float smag = sqrtf(vdot<NS>(search, search)) * m.meaninertia * nvf;
+      float smag = RR_SQRT(vdot<NS>(search, search)) * m.meaninertia * nvf;
       float gtol = m.tolerance * m.ls_tolerance * smag;
       /* mv = M search.  search = -Mgrad + beta search_prev with M Mgrad = grad (Mgrad is the LD solve of grad), so
        * mv = -grad + beta mv_prev: the same vector MJX gets from mul_m(search), without the product. */

@@ -122,6 +122,8 @@ typedef const char *rr_emu_saddr;
 #define RR_SADDR(p) ((rr_emu_saddr)(p))
 #define RR_SLOAD(a) (*(const float *)(a))
 #define RR_RCP(x) (1.f / (x))
+#define RR_SQRT(x) sqrtf(x)
+#define RR_SINCOS(x, s, c) sincosf(x, s, c)
 #define RR_SOLVE_UPDATE(x, m, bit, a, xi) do { if ((m) & (bit)) (x) -= RR_SLOAD(a) * (xi); } while (0)
 
 #include "../../brax_rodent_run_b200/csrc/rr_kernels.inl"
