@@ -553,11 +553,12 @@ RR_DEV void crb_and_mass_matrix(Ctx<NS> &c) {
   const RRModelDev &m = c.m;
   for (int i = c.lane; i < 10 * m.nbody; i += 32) c.crb[i] = c.cinert[i];
   __syncwarp();
+  /* lane q owns component q of every body: no cross-lane hazard, so no rendezvous inside the loop */
   for (int b = m.nbody - 1; b > 0; b--) {
     int p = RI(body_parentid, b);
     if (c.lane < 10 && p > 0) c.crb[10 * p + c.lane] += c.crb[10 * b + c.lane];
-    __syncwarp();
   }
+  __syncwarp();
   /* row i of qM: f = crb[body(i)] * cdof[i], then M(i, a) = cdof[a] . f for every ancestor-or-self a of i */
   RR_FOR_S {
     int i = c.lane + 32 * s;
@@ -889,11 +890,11 @@ RR_DEV void com_vel_and_rne(Ctx<NS> &c, float (&qfrc_bias)[NS]) {
     for (int k = 0; k < 6; k++) c.cfrc[6 * b + k] = f1[k] + f3[k]; /* cfrc aliases cacc: body-local, in place */
   }
   __syncwarp();
-  for (int b = m.nbody - 1; b > 0; b--) {
+  for (int b = m.nbody - 1; b > 0; b--) { /* lane q owns component q: no rendezvous needed inside the loop */
     int p = RI(body_parentid, b);
     if (c.lane < 6 && p > 0) c.cfrc[6 * p + c.lane] += c.cfrc[6 * b + c.lane];
-    __syncwarp();
   }
+  __syncwarp();
   RR_FOR_S {
     int i = c.lane + 32 * s;
     float v = 0.f;
