@@ -44,8 +44,9 @@ struct RRSmem {
   int M, LD;                                               /* B */
   int xpos, xquat, cdof;                                   /* C, live through the Jacobian build */
   int cinert, qfrc_act, cvel, cacc, cfrc, crb, fcrb;       /* C1 */
-  int con_dist, cab, cscr, cbv, cact, ckidx, row_D; /* C2: cab = 18 floats per contact; rows: D aref Jaref jv id, capR each */
-  int capR;
+  int con_dist, cab, cscr, cbv, cact, ckidx, row_D; /* C2: cab = 12 floats per contact (frame, point - COM); cscr = 6 floats per
+                                                       ACTIVE contact (capA in shared memory); rows: D aref Jaref jv id, capR each */
+  int capR, capA;
   int total; /* floats per environment */
 };
 
@@ -106,7 +107,7 @@ struct RRStepArgs {
   const int *env_order; /* [slots] slot -> env (-1 idle) or null */
   RRDebug dbg;
   float *scratch;     /* [warp slots, scratch_stride] global overflow for contact Jacobians / constraint rows */
-  int scratch_stride; /* floats: 5 align4(nefc) */
+  int scratch_stride; /* floats: 5 align4(nefc) + 8 + 6 align4(ncon) */
   long long *prof; /* [B, RR_NPROF] clock64 deltas or null */
 };
 

@@ -985,6 +985,7 @@ RR_DEV void collision(Ctx<NS> &c) {
   const RRModelDev &m = c.m;
   for (int p = c.lane; p < m.npair; p += 32) {
     int b = RI(pair_body, p), ca = RI(pair_conadr, p), fn = RI(pair_fn, p);
+    const float *cm = c.com + 3 * RI(body_rootslot, b); /* contact points are kept relative to the tree COM (what cdof refers to) */
     float n[3], pp[3], gl[3], gq[4], xq[4], gp[3], r[3], size[3];
 #pragma unroll
     for (int k = 0; k < 3; k++) {
@@ -1001,8 +1002,8 @@ RR_DEV void collision(Ctx<NS> &c) {
       float dist = dot3(d, n) - size[0];
       c.con_dist[ca] = dist;
 #pragma unroll
-      for (int k = 0; k < 3; k++) c.cab[18 * ca + 9 + k] = gp[k] - n[k] * (size[0] + 0.5f * dist);
-      make_frame(c.cab + 18 * ca, n);
+      for (int k = 0; k < 3; k++) c.cab[12 * ca + 9 + k] = gp[k] - n[k] * (size[0] + 0.5f * dist) - cm[k];
+      make_frame(c.cab + 12 * ca, n);
     } else {
       float q[4], gm[9];
       quat_mul(q, xq, gq);
@@ -1028,9 +1029,9 @@ RR_DEV void collision(Ctx<NS> &c) {
           float dist = dot3(d, n) - size[0];
           c.con_dist[ca + e] = dist;
 #pragma unroll
-          for (int k = 0; k < 3; k++) c.cab[18 * (ca + e) + 9 + k] = cp[k] - n[k] * (size[0] + 0.5f * dist);
+          for (int k = 0; k < 3; k++) c.cab[12 * (ca + e) + 9 + k] = cp[k] - n[k] * (size[0] + 0.5f * dist) - cm[k];
 #pragma unroll
-          for (int k = 0; k < 9; k++) c.cab[18 * (ca + e) + k] = frame[k];
+          for (int k = 0; k < 9; k++) c.cab[12 * (ca + e) + k] = frame[k];
         }
       } else { /* plane - ellipsoid */
         float nl[3], sv[3], lp[3], wp[3];
@@ -1047,8 +1048,8 @@ RR_DEV void collision(Ctx<NS> &c) {
         float dist = dot3(d, n);
         c.con_dist[ca] = dist;
 #pragma unroll
-        for (int k = 0; k < 3; k++) c.cab[18 * ca + 9 + k] = wp[k] - n[k] * dist * 0.5f;
-        make_frame(c.cab + 18 * ca, n);
+        for (int k = 0; k < 3; k++) c.cab[12 * ca + 9 + k] = wp[k] - n[k] * dist * 0.5f - cm[k];
+        make_frame(c.cab + 12 * ca, n);
       }
     }
   }
@@ -1056,18 +1057,24 @@ RR_DEV void collision(Ctx<NS> &c) {
   dbg_copy<NS>(c, RR_DBG_CON_DIST, c.con_dist, m.ncon);
   if (RR_WITH_DEBUG && c.dbg) {
     float *dP = c.dbg + dbg_offset(m, RR_DBG_CON_POS), *dF = c.dbg + dbg_offset(m, RR_DBG_CON_FRAME);
-    for (int i = c.lane; i < 3 * m.ncon; i += 32) dP[i] = c.cab[18 * (i / 3) + 9 + i % 3];
-    for (int i = c.lane; i < 9 * m.ncon; i += 32) dF[i] = c.cab[18 * (i / 9) + i % 9];
+    for (int i = c.lane; i < 3 * m.ncon; i += 32) {
+      int cc = i / 3, k = i % 3;
+      dP[i] = c.cab[12 * cc + 9 + k] + c.com[3 * RI(body_rootslot, RI(pair_body, RI(con_pair, cc))) + k];
+    }
+    for (int i = c.lane; i < 9 * m.ncon; i += 32) dF[i] = c.cab[12 * (i / 9) + i % 9];
   }
 }
 
 /* ------------------------------------------------------------------------------------------ constraint rows (B.5) */
 /* Contact Jacobians are never materialised.  A contact row in frame direction r is
  *   J_r[d] = fr_r . (cdof_lin[d] + cdof_ang[d] x off) = [off x fr_r ; fr_r] . cdof[d]        (off = contact point - tree COM)
- * so each contact keeps 3 six-vectors cab[c][r] = [off x fr_r ; fr_r] (18 floats, always in shared memory), and
- *   J v   = cab . V_b,   V_b = sum over the chain of body b of cdof[d] v[d]     (spatial velocity induced by v)
- *   J' f  : F_b = sum over contacts on b of g_r cab[c][r],  qfc[d] = cdof[d] . F_b for d in chain(b)
- * with one V_b / F_b per contact BODY (10 for the rodent's 34 contacts): work no longer scales with chain x contacts. */
+ * Each contact keeps its frame and off (cab: 12 floats), and
+ *   J v   : V_b = sum over the chain of body b of cdof[d] v[d] (spatial velocity induced by v), u = V_lin + V_ang x off,
+ *           (J v)_r = fr_r . u
+ *   J' f  : per contact the world force w = sum_r g_r fr_r and its moment off x w about the tree COM (six floats, cscr),
+ *           F_b = their sum over the contacts on b,  qfc[d] = cdof[d] . F_b for d in chain(b)
+ * with one V_b / F_b per contact BODY (10 for the rodent's 34 contacts): work no longer scales with chain x contacts.
+ * cscr holds six floats per ACTIVE contact (compact index), in shared memory up to capA contacts. */
 
 /* rows: out[r] = J_r . v for the compact active rows; v staged in vbuf by the caller (already synced). */
 template <int NS>
@@ -1092,18 +1099,23 @@ RR_DEV void mul_j(Ctx<NS> &c, float *out) {
     c.cbv[it] = acc;
   }
   __syncwarp();
-  for (int it = c.lane; it < 3 * c.nca; it += 32) {
-    int k = it / 3, r3 = it - 3 * k;
-    int cc = c.cact[k];
-    const float *ab = c.cab + 18 * cc + 6 * r3, *V = c.cbv + 6 * RI(pair_cb, RI(con_pair, cc));
-    c.cscr[it] = ab[0] * V[0] + ab[1] * V[1] + ab[2] * V[2] + ab[3] * V[3] + ab[4] * V[4] + ab[5] * V[5];
+  for (int k = c.lane; k < c.nca; k += 32) {
+    const int cc = c.cact[k];
+    const float *ab = c.cab + 12 * cc, *V = c.cbv + 6 * RI(pair_cb, RI(con_pair, cc));
+    const float off[3] = {ab[9], ab[10], ab[11]}, va[3] = {V[0], V[1], V[2]};
+    float u[3];
+    cross3(u, va, off);
+#pragma unroll
+    for (int q = 0; q < 3; q++) u[q] += V[3 + q];
+#pragma unroll
+    for (int r3 = 0; r3 < 3; r3++) c.cscr[6 * k + r3] = ab[3 * r3] * u[0] + ab[3 * r3 + 1] * u[1] + ab[3 * r3 + 2] * u[2];
   }
   __syncwarp();
   for (int r = c.lane; r < 4 * c.nca; r += 32) {
     int k = r >> 2, q = r & 3;
     float mu = RF(pair_mu, RI(con_pair, c.cact[k]));
     float f = (q & 1) ? -mu : mu;
-    out[c.nla + r] = c.cscr[3 * k] + c.cscr[3 * k + 1 + (q >> 1)] * f;
+    out[c.nla + r] = c.cscr[6 * k] + c.cscr[6 * k + 1 + (q >> 1)] * f;
   }
   __syncwarp();
 }
@@ -1122,10 +1134,17 @@ RR_DEV void mul_jt(Ctx<NS> &c, const float *frc, float (&qfc)[NS]) {
   }
   for (int k = c.lane; k < c.nca; k += 32) {
     const float *f = frc + c.nla + 4 * k;
-    float mu = RF(pair_mu, RI(con_pair, c.cact[k]));
-    c.cscr[3 * k] = f[0] + f[1] + f[2] + f[3];
-    c.cscr[3 * k + 1] = mu * f[0] - mu * f[1];
-    c.cscr[3 * k + 2] = mu * f[2] - mu * f[3];
+    const int cc = c.cact[k];
+    const float mu = RF(pair_mu, RI(con_pair, cc));
+    const float g0 = f[0] + f[1] + f[2] + f[3], g1 = mu * f[0] - mu * f[1], g2 = mu * f[2] - mu * f[3];
+    const float *ab = c.cab + 12 * cc;
+    float w[3], t[3];
+#pragma unroll
+    for (int q = 0; q < 3; q++) w[q] = g0 * ab[q] + g1 * ab[3 + q] + g2 * ab[6 + q];
+    const float off[3] = {ab[9], ab[10], ab[11]};
+    cross3(t, off, w);
+#pragma unroll
+    for (int q = 0; q < 3; q++) { c.cscr[6 * k + q] = t[q]; c.cscr[6 * k + 3 + q] = w[q]; }
   }
   __syncwarp();
   /* F_b: item = (body slot, component), summed over that body's (static) contact list; ckidx maps a contact to its
@@ -1138,10 +1157,7 @@ RR_DEV void mul_jt(Ctx<NS> &c, const float *frc, float (&qfc)[NS]) {
     for (int e = beg; e < end; e++) {
       int cc = RI(cb_conlist, e);
       int k = c.ckidx[cc];
-      if (k >= 0) {
-        const float *ab = c.cab + 18 * cc + q;
-        acc += c.cscr[3 * k] * ab[0] + c.cscr[3 * k + 1] * ab[6] + c.cscr[3 * k + 2] * ab[12];
-      }
+      if (k >= 0) acc += c.cscr[6 * k + q];
     }
     c.cbv[it] = acc;
   }
@@ -1201,6 +1217,7 @@ RR_DEV void make_constraint(Ctx<NS> &c) {
   c.nla = nla;
   c.nca = nca;
   c.use_rows(nra <= m.sm.capR);
+  c.cscr = nca <= m.sm.capA ? c.sm_base + m.sm.cscr : c.grows + 5 * m.nefc + 4; /* six floats per active contact */
   __syncwarp();
   /* pass 2: limit rows */
   int r0 = 0;
@@ -1230,24 +1247,10 @@ RR_DEV void make_constraint(Ctx<NS> &c) {
     }
     r0 += __popc(mask);
   }
-  /* active contacts: (frame, pos) -> cab = [off x fr_r ; fr_r], r = 0..2, in place; row parameters */
+  /* active contacts: row parameters (the frame and the point stay as collision() left them) */
   for (int k = c.lane; k < nca; k += 32) {
     int cc = c.cact[k];
     int p = RI(con_pair, cc);
-    int rs = RI(body_rootslot, RI(pair_body, p));
-    float *ab = c.cab + 18 * cc;
-    float fr[9], off[3];
-#pragma unroll
-    for (int q = 0; q < 9; q++) fr[q] = ab[q];
-#pragma unroll
-    for (int q = 0; q < 3; q++) off[q] = ab[9 + q] - c.com[3 * rs + q];
-#pragma unroll
-    for (int r3 = 0; r3 < 3; r3++) {
-      float x[3];
-      cross3(x, off, fr + 3 * r3);
-#pragma unroll
-      for (int q = 0; q < 3; q++) { ab[6 * r3 + q] = x[q]; ab[6 * r3 + 3 + q] = fr[3 * r3 + q]; }
-    }
     float pos = c.con_dist[cc] - RF(pair_margin, p);
     float sr[2] = {RF(pair_solref, 2 * p), RF(pair_solref, 2 * p + 1)}, si[5], kk, b, imp;
 #pragma unroll
@@ -1282,15 +1285,18 @@ RR_DEV void make_constraint(Ctx<NS> &c) {
       int p = RI(con_pair, cc);
       int ld = RI(pair_lastdof, p);
       int len = RI(dof_depth, ld) + 1, adr = RI(dof_rowadr, ld);
-      const float *ab = c.cab + 18 * cc;
+      const float *ab = c.cab + 12 * cc;
+      const float off[3] = {ab[9], ab[10], ab[11]};
       float mu = RF(pair_mu, p);
       for (int t = c.lane; t < len; t += 32) {
         int d = RR_META_COL(RI(M_meta, adr + t));
         const float *cd = c.cdof + 6 * d;
         float j3[3];
         for (int r3 = 0; r3 < 3; r3++) {
+          float x[3];
+          cross3(x, off, ab + 3 * r3);
           j3[r3] = 0.f;
-          for (int q = 0; q < 6; q++) j3[r3] += ab[6 * r3 + q] * cd[q];
+          for (int q = 0; q < 3; q++) j3[r3] += x[q] * cd[q] + ab[3 * r3 + q] * cd[3 + q];
         }
         for (int q = 0; q < 4; q++) {
           float f = (q & 1) ? -mu : mu;

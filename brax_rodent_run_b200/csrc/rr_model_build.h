@@ -369,7 +369,8 @@ inline void rr_host_model_build(RRHostModel &hm, const int32_t *dir, const int32
   c1_end = std::max(c1_end, o);
   /* C2: contact arrays, then as many constraint rows (5 arrays) as fit in the recycled span */
   o = c0;
-  s.con_dist = take(nc); s.cab = take(18 * nc); s.cscr = take(3 * nc); s.cbv = take(6 * d.ncb); s.cact = take(nc); s.ckidx = take(nc);
+  s.capA = std::min(nc, 32); /* active contacts whose six-vectors stay in shared memory (more go to the global scratch) */
+  s.con_dist = take(nc); s.cab = take(12 * nc); s.cscr = take(6 * s.capA); s.cbv = take(6 * d.ncb); s.cact = take(nc); s.ckidx = take(nc);
   int avail = c1_end - o;
   int capR = std::min((d.nefc + 3) & ~3, std::max(avail / 5, 32) & ~3);
   if (capR < 4) capR = 4;
