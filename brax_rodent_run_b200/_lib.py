@@ -42,6 +42,16 @@ class RRBuffers(ctypes.Structure):
     _fields_ = [(n, vp) for n in _BUF_FIELDS]
 
 
+class RRPpoLossArgs(ctypes.Structure):
+    """rr_ppo_loss_args (include/rr_b200.h)."""
+    _fields_ = ([(n, ctypes.c_int32) for n in ("T", "B", "A")] +
+                [(n, vp) for n in ("logits", "baseline", "bootstrap", "raw_action", "old_log_prob", "reward", "discount",
+                                   "truncation", "noise")] +
+                [(n, ctypes.c_float) for n in ("reward_scaling", "discounting", "gae_lambda", "clipping_epsilon", "entropy_cost")] +
+                [("normalize_advantage", ctypes.c_int32)] +
+                [(n, vp) for n in ("scratch", "adv_partial", "loss_partial", "grad_logits", "grad_baseline")])
+
+
 _libs = {}
 
 
@@ -72,6 +82,8 @@ def load(path: Optional[str] = None):
     L.rr_env_step.argtypes = [vp, ctypes.POINTER(RRBuffers), vp, ctypes.c_int32, vp]
     L.rr_env_step_host.argtypes = [vp, ctypes.POINTER(RRBuffers), vp, ctypes.c_int32, vp, vp, vp, vp]
     L.rr_gae.argtypes = [vp, vp, vp, vp, vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_float, ctypes.c_float, vp, vp, vp]
+    L.rr_ppo_loss_blocks.argtypes = [ctypes.c_int32, ctypes.c_int32, c_i, c_i]
+    L.rr_ppo_loss.argtypes = [ctypes.POINTER(RRPpoLossArgs), vp]
     L.rr_debug_field.argtypes = [vp, ctypes.c_char_p, c_i, c_i]
     L.rr_env_set_debug.argtypes = [vp, vp]
     L.rr_env_set_profile.argtypes = [vp, vp]
@@ -81,7 +93,7 @@ def load(path: Optional[str] = None):
     L.rr_launch_count.restype = ctypes.c_longlong
     for name in ("rr_model_create", "rr_model_set_solver", "rr_model_dims", "rr_env_create", "rr_env_set_task",
                  "rr_env_set_wrappers", "rr_env_geometry", "rr_env_init", "rr_env_step", "rr_env_step_host", "rr_gae", "rr_debug_field",
-                 "rr_env_set_debug", "rr_env_set_profile"):
+                 "rr_env_set_debug", "rr_env_set_profile", "rr_ppo_loss", "rr_ppo_loss_blocks"):
         getattr(L, name).restype = ctypes.c_int
     _libs[path] = L
     return L

@@ -96,6 +96,42 @@ __global__ void rr_gae_kernel(const float *__restrict__ rewards, const float *__
   }
 }
 
+/* ---- fused PPO loss (rr_ppo_loss.h): stage A one thread per environment column, stage B one thread per (t, env) element ---- */
+#include "rr_ppo_loss.h"
+#define RR_PPO_THREADS 128
+__global__ void __launch_bounds__(RR_PPO_THREADS) rr_ppo_loss_a_kernel(const __grid_constant__ RRPpoLossArgs a) {
+  __shared__ double sh1[RR_PPO_THREADS], sh2[RR_PPO_THREADS];
+  const int b = blockIdx.x * RR_PPO_THREADS + threadIdx.x;
+  double s1 = 0.0, s2 = 0.0;
+  if (b < a.B) rr_ppo_stage_a(a, b, s1, s2);
+  sh1[threadIdx.x] = s1; sh2[threadIdx.x] = s2;
+  __syncthreads();
+  for (int o = RR_PPO_THREADS / 2; o > 0; o >>= 1) { /* fixed-order tree: deterministic */
+    if (threadIdx.x < o) { sh1[threadIdx.x] += sh1[threadIdx.x + o]; sh2[threadIdx.x] += sh2[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { a.adv_partial[2 * blockIdx.x] = sh1[0]; a.adv_partial[2 * blockIdx.x + 1] = sh2[0]; }
+}
+__global__ void __launch_bounds__(RR_PPO_THREADS) rr_ppo_loss_b_kernel(const __grid_constant__ RRPpoLossArgs a) {
+  __shared__ float sh[3][RR_PPO_THREADS];
+  double s1 = 0.0, s2 = 0.0;
+  for (int k = 0; k < a.nblkA; k++) { s1 += a.adv_partial[2 * k]; s2 += a.adv_partial[2 * k + 1]; }
+  const double n = (double)a.T * (double)a.B, mean = s1 / n;
+  double var = s2 / n - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const size_t i = (size_t)blockIdx.x * RR_PPO_THREADS + threadIdx.x;
+  float pol = 0.f, val = 0.f, ent = 0.f;
+  if (i < (size_t)a.T * a.B) rr_ppo_stage_b(a, i, (float)mean, (float)sqrt(var), pol, val, ent);
+  sh[0][threadIdx.x] = pol; sh[1][threadIdx.x] = val; sh[2][threadIdx.x] = ent;
+  __syncthreads();
+  for (int o = RR_PPO_THREADS / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o)
+      for (int q = 0; q < 3; q++) sh[q][threadIdx.x] += sh[q][threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x < 3) a.loss_partial[3 * blockIdx.x + threadIdx.x] = sh[threadIdx.x][0];
+}
+
 static thread_local char g_cuda_err[256];
 static const char *rrb_error() { return g_cuda_err; }
 static int rrb_check(cudaError_t e, const char *what) {
@@ -177,6 +213,13 @@ static int rrb_launch_gae(const float *rewards, const float *values, const float
   rr_gae_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(rewards, values, bootstrap, termination, truncation, T, B,
                                                                   discount, lambda_, vs, adv);
   return rrb_check(cudaGetLastError(), "rr_gae_kernel launch");
+}
+
+static int rrb_ppo_blocks(int n) { return (n + RR_PPO_THREADS - 1) / RR_PPO_THREADS; }
+static int rrb_launch_ppo_loss(const RRPpoLossArgs &a, void *stream) {
+  rr_ppo_loss_a_kernel<<<rrb_ppo_blocks(a.B), RR_PPO_THREADS, 0, (cudaStream_t)stream>>>(a);
+  rr_ppo_loss_b_kernel<<<rrb_ppo_blocks(a.T * a.B), RR_PPO_THREADS, 0, (cudaStream_t)stream>>>(a);
+  return rrb_check(cudaGetLastError(), "rr_ppo_loss launch");
 }
 
 #include "rr_api_impl.inl"

@@ -20,6 +20,7 @@
 
 #include "../../include/rr_b200.h"
 #include "rr_model_build.h"
+#include "rr_ppo_loss.h"
 
 static thread_local std::string g_rr_error;
 static std::atomic<long long> g_rr_launches{0};
@@ -305,5 +306,35 @@ extern "C" int rr_gae(const float *rewards, const float *values, const float *bo
   if (rrb_launch_gae(rewards, values, bootstrap_value, termination, truncation, T, B, discount, lambda_, vs, advantages, stream))
     return rr_fail(RR_ECUDA, rrb_error());
   g_rr_launches++;
+  return RR_OK;
+}
+
+
+extern "C" int rr_ppo_loss_blocks(int32_t T, int32_t B, int32_t *blocks_a, int32_t *blocks_b) {
+  if (T < 1 || B < 1 || !blocks_a || !blocks_b) return rr_fail(RR_EINVAL, "rr_ppo_loss_blocks: bad argument");
+  *blocks_a = rrb_ppo_blocks(B);
+  *blocks_b = rrb_ppo_blocks(T * B);
+  return RR_OK;
+}
+
+extern "C" int rr_ppo_loss(const rr_ppo_loss_args *u, void *stream) {
+  if (!u) return rr_fail(RR_EINVAL, "rr_ppo_loss: null argument");
+  if (u->T < 1 || u->B < 1 || u->A < 1 || !u->logits || !u->baseline || !u->bootstrap || !u->raw_action || !u->old_log_prob ||
+      !u->reward || !u->discount || !u->truncation || !u->noise || !u->scratch || !u->adv_partial || !u->loss_partial ||
+      !u->grad_logits || !u->grad_baseline)
+    return rr_fail(RR_EINVAL, "rr_ppo_loss: bad argument");
+  RRPpoLossArgs a;
+  a.T = u->T; a.B = u->B; a.A = u->A;
+  a.logits = u->logits; a.baseline = u->baseline; a.bootstrap = u->bootstrap; a.raw_action = u->raw_action;
+  a.old_log_prob = u->old_log_prob; a.reward = u->reward; a.discount = u->discount; a.truncation = u->truncation; a.noise = u->noise;
+  a.reward_scaling = u->reward_scaling; a.gamma = u->discounting; a.lambda_ = u->gae_lambda; a.clip_eps = u->clipping_epsilon;
+  a.entropy_cost = u->entropy_cost; a.normalize_advantage = u->normalize_advantage;
+  const size_t n = (size_t)u->T * u->B;
+  a.lp = u->scratch; a.adv = u->scratch + n; a.vs = u->scratch + 2 * n;
+  a.adv_partial = u->adv_partial; a.loss_partial = u->loss_partial;
+  a.grad_logits = u->grad_logits; a.grad_baseline = u->grad_baseline;
+  a.nblkA = rrb_ppo_blocks(u->B);
+  if (rrb_launch_ppo_loss(a, stream)) return rr_fail(RR_ECUDA, rrb_error());
+  g_rr_launches += 2;
   return RR_OK;
 }

@@ -51,6 +51,7 @@ class PPOConfig:
     num_eval_envs: int = 128
     deterministic_eval: bool = False
     seed: int = 0
+    fused_loss: bool = True         # loss + gradient w.r.t. the network outputs in two hand-written kernels (rr_ppo_loss)
     cuda_graph: bool = True         # replay the minibatch update (loss, backward, Adam) as one CUDA graph on CUDA devices
     tf32: bool = True               # TF32 tensor-core matmuls, as XLA's default float32 dot precision on NVIDIA GPUs
     policy_hidden: tuple = (32, 32, 32, 32)
@@ -121,24 +122,32 @@ def tanh_normal_sample(logits: torch.Tensor, gen: Optional[torch.Generator] = No
     return torch.tanh(raw), raw, tanh_normal_log_prob(logits, raw)
 
 
-def tanh_normal_log_prob(logits: torch.Tensor, raw: torch.Tensor) -> torch.Tensor:
-    loc, scale = logits.chunk(2, dim=-1)
-    scale = F.softplus(scale) + 1e-3
-    lp = -0.5 * ((raw - loc) / scale) ** 2 - torch.log(scale) - 0.5 * math.log(2 * math.pi)
-    lp = lp - 2.0 * (_LOG2 - raw - F.softplus(-2.0 * raw))  # tanh log-det-jacobian
-    return lp.sum(-1)
+def tanh_normal_params(logits: torch.Tensor):
+    """(loc, scale, log scale) of NormalTanhDistribution; contiguous halves so that the element-wise kernels that follow are
+    the vectorised ones (a strided `chunk` view sends every one of them down the generic strided path)."""
+    a = logits.shape[-1] // 2
+    loc, pre = logits[..., :a].contiguous(), logits[..., a:].contiguous()
+    scale = F.softplus(pre) + 1e-3
+    return loc, scale, torch.log(scale)
+
+
+def _log_det_tanh(raw: torch.Tensor) -> torch.Tensor:
+    return 2.0 * (_LOG2 - raw - F.softplus(-2.0 * raw))
+
+
+def tanh_normal_log_prob(logits: torch.Tensor, raw: torch.Tensor, params=None) -> torch.Tensor:
+    loc, scale, log_scale = params if params is not None else tanh_normal_params(logits)
+    lp = -0.5 * ((raw - loc) / scale) ** 2 - log_scale - 0.5 * math.log(2 * math.pi)
+    return (lp - _log_det_tanh(raw)).sum(-1)
 
 
 def tanh_normal_entropy(logits: torch.Tensor, gen: Optional[torch.Generator] = None,
-                        noise: Optional[torch.Tensor] = None) -> torch.Tensor:
-    loc, scale = logits.chunk(2, dim=-1)
-    scale = F.softplus(scale) + 1e-3
-    ent = 0.5 + 0.5 * math.log(2 * math.pi) + torch.log(scale)
+                        noise: Optional[torch.Tensor] = None, params=None) -> torch.Tensor:
+    loc, scale, log_scale = params if params is not None else tanh_normal_params(logits)
     if noise is None:
         noise = torch.randn(loc.shape, device=loc.device, generator=gen)
     raw = loc + scale * noise
-    ent = ent + 2.0 * (_LOG2 - raw - F.softplus(-2.0 * raw))
-    return ent.sum(-1)
+    return (0.5 + 0.5 * math.log(2 * math.pi) + log_scale + _log_det_tanh(raw)).sum(-1)
 
 
 def compute_gae(L, truncation, termination, rewards, values, bootstrap, lambda_, discount):
@@ -150,6 +159,49 @@ def compute_gae(L, truncation, termination, rewards, values, bootstrap, lambda_,
     _lib.check(L, L.rr_gae(p(rewards.contiguous()), p(values.contiguous()), p(bootstrap.contiguous()), p(termination.contiguous()),
                            p(truncation.contiguous()), T, B, discount, lambda_, p(vs), p(adv), stream))
     return vs, adv
+
+
+class _FusedPPOLoss(torch.autograd.Function):
+    """total loss of one minibatch through rr_ppo_loss; backward hands the kernel's analytic d loss / d (logits, baseline)
+    to autograd, which continues through the two MLPs.  Returns (total, policy_loss, v_loss, entropy_loss)."""
+
+    @staticmethod
+    def forward(ctx, logits, baseline, bootstrap, mb, noise, cfg, L):
+        T, B = baseline.shape
+        A = logits.shape[-1] // 2
+        dev = logits.device
+        c = lambda x: x.detach().contiguous()
+        logits_c, baseline_c = c(logits), c(baseline)
+        ba, bb = ctypes.c_int32(), ctypes.c_int32()
+        _lib.check(L, L.rr_ppo_loss_blocks(T, B, ctypes.byref(ba), ctypes.byref(bb)))
+        scratch = torch.empty(3 * T * B, device=dev)
+        adv_partial = torch.empty(2 * ba.value, device=dev, dtype=torch.float64)
+        loss_partial = torch.empty((bb.value, 3), device=dev)
+        grad_logits, grad_baseline = torch.empty_like(logits_c), torch.empty_like(baseline_c)
+        keep = [logits_c, baseline_c, c(bootstrap), c(mb["raw_action"]), c(mb["log_prob"]), c(mb["reward"]), c(mb["discount"]),
+                c(mb["truncation"]), c(noise)]
+        a = _lib.RRPpoLossArgs()
+        a.T, a.B, a.A = T, B, A
+        for name, t in zip(("logits", "baseline", "bootstrap", "raw_action", "old_log_prob", "reward", "discount", "truncation",
+                            "noise"), keep):
+            assert t.dtype == torch.float32
+            setattr(a, name, t.data_ptr())
+        a.reward_scaling, a.discounting, a.gae_lambda = cfg.reward_scaling, cfg.discounting, cfg.gae_lambda
+        a.clipping_epsilon, a.entropy_cost, a.normalize_advantage = cfg.clipping_epsilon, cfg.entropy_cost, int(cfg.normalize_advantage)
+        a.scratch, a.adv_partial, a.loss_partial = scratch.data_ptr(), adv_partial.data_ptr(), loss_partial.data_ptr()
+        a.grad_logits, a.grad_baseline = grad_logits.data_ptr(), grad_baseline.data_ptr()
+        stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream) if logits.is_cuda else None
+        _lib.check(L, L.rr_ppo_loss(ctypes.byref(a), stream))
+        terms = loss_partial.sum(0) / float(T * B)
+        policy_loss, v_loss, entropy_loss = terms[0], terms[1], -cfg.entropy_cost * terms[2]
+        ctx.save_for_backward(grad_logits, grad_baseline)
+        ctx.mark_non_differentiable(policy_loss, v_loss, entropy_loss)
+        return policy_loss + v_loss + entropy_loss, policy_loss, v_loss, entropy_loss
+
+    @staticmethod
+    def backward(ctx, g_total, *_):
+        grad_logits, grad_baseline = ctx.saved_tensors
+        return g_total * grad_logits, g_total * grad_baseline, None, None, None, None, None
 
 
 class PPO:
@@ -169,8 +221,9 @@ class PPO:
         if self.device.type == "cuda" and cfg.tf32:
             torch.backends.cuda.matmul.allow_tf32 = True
             torch.backends.cudnn.allow_tf32 = True
+        cuda = self.device.type == "cuda"
         self.opt = torch.optim.Adam(self.params, lr=cfg.learning_rate, eps=1e-8, capturable=self._use_graph,
-                                    foreach=True if self.device.type == "cuda" else None)
+                                    fused=True if cuda else None)  # one multi-tensor kernel instead of ~15 foreach launches
         self._graph = None          # (fwd + bwd [+ Adam]) graph, static minibatch buffers, static metrics
         self._graph_warm = 0
         self.normalizer = RunningStats(obs, self.device)
@@ -214,6 +267,14 @@ class PPO:
         obs = self._norm(mb["observation"])                      # [T, b, obs]
         logits = self.policy(obs)
         baseline = self.value(obs).squeeze(-1)
+        if cfg.fused_loss:
+            with torch.no_grad():
+                bootstrap = self.value(self._norm(mb["next_observation_last"])).squeeze(-1)
+                noise = mb.get("entropy_noise")
+                if noise is None:
+                    noise = torch.randn(mb["raw_action"].shape, device=obs.device, generator=self.gen)
+            total, policy_loss, v_loss, entropy_loss = _FusedPPOLoss.apply(logits, baseline, bootstrap, mb, noise, cfg, self.env._L)
+            return total, dict(total_loss=total.detach(), policy_loss=policy_loss, v_loss=v_loss, entropy_loss=entropy_loss)
         with torch.no_grad():
             bootstrap = self.value(self._norm(mb["next_observation_last"])).squeeze(-1)
             rewards = mb["reward"] * cfg.reward_scaling
@@ -223,12 +284,13 @@ class PPO:
                                   cfg.discounting)
             if cfg.normalize_advantage:
                 adv = (adv - adv.mean()) / (adv.std(unbiased=False) + 1e-8)
-        target_lp = tanh_normal_log_prob(logits, mb["raw_action"])
+        dist_params = tanh_normal_params(logits)
+        target_lp = tanh_normal_log_prob(logits, mb["raw_action"], dist_params)
         rho = torch.exp(target_lp - mb["log_prob"])
         s1, s2 = rho * adv, rho.clamp(1 - cfg.clipping_epsilon, 1 + cfg.clipping_epsilon) * adv
         policy_loss = -torch.min(s1, s2).mean()
         v_loss = ((vs - baseline) ** 2).mean() * 0.5 * 0.5
-        entropy = tanh_normal_entropy(logits, self.gen, mb.get("entropy_noise")).mean()
+        entropy = tanh_normal_entropy(logits, self.gen, mb.get("entropy_noise"), dist_params).mean()
         entropy_loss = -cfg.entropy_cost * entropy
         total = policy_loss + v_loss + entropy_loss
         return total, dict(total_loss=total.detach(), policy_loss=policy_loss.detach(), v_loss=v_loss.detach(),

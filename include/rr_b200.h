@@ -117,6 +117,27 @@ int rr_gae(const float *rewards, const float *values, const float *bootstrap_val
            const float *truncation, int32_t T, int32_t B, float discount, float lambda_, float *vs, float *advantages,
            void *stream);
 
+/* Fused PPO minibatch loss + gradient w.r.t. the network outputs.  Replaces, for one minibatch, what brax's
+ * ppo.losses.compute_ppo_loss computes under jax.grad inside ppo.train (brax_rodent_run_ppo.py:97-114, 200): tanh-normal
+ * log-prob, compute_gae, advantage normalisation, clipped surrogate, 0.25 * mse value loss, sampled entropy.
+ * All pointers are device pointers, time-major [T, B, ...] contiguous fp32 (adv_partial: double).
+ *   scratch       [3 T B]           work space (log-prob, advantages, vs)
+ *   adv_partial   [2 blocks_a]      doubles; loss_partial [3 blocks_b]: per-block sums of (policy, value, entropy) terms --
+ *                                   the caller divides their column sums by T B (rr_ppo_loss_blocks gives the block counts)
+ *   grad_logits   [T, B, 2 A], grad_baseline [T, B]: d total_loss / d output, total = policy + value - entropy_cost * entropy */
+typedef struct rr_ppo_loss_args {
+  int32_t T, B, A;
+  const float *logits, *baseline, *bootstrap, *raw_action, *old_log_prob, *reward, *discount, *truncation, *noise;
+  float reward_scaling, discounting, gae_lambda, clipping_epsilon, entropy_cost;
+  int32_t normalize_advantage;
+  float *scratch;
+  double *adv_partial;
+  float *loss_partial, *grad_logits, *grad_baseline;
+} rr_ppo_loss_args;
+int rr_ppo_loss_blocks(int32_t T, int32_t B, int32_t *blocks_a, int32_t *blocks_b);
+int rr_ppo_loss(const rr_ppo_loss_args *args, void *stream);
+
+
 /* Parity-test hooks: per-environment dump of forward-pass intermediates (tests only). */
 int rr_debug_field(const rr_model *m, const char *name, int32_t *offset, int32_t *count);
 int rr_env_set_debug(rr_env *e, float *dbg /* DEVICE [B, debug_stride] or null */);

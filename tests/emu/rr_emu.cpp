@@ -179,4 +179,36 @@ static int rrb_launch_gae(const float *rewards, const float *values, const float
   return 0;
 }
 
+#define RR_PPO_HD static inline
+#include "../../brax_rodent_run_b200/csrc/rr_ppo_loss.h"
+static int rrb_ppo_blocks(int n) { return (n + 127) / 128; }
+static int rrb_launch_ppo_loss(const RRPpoLossArgs &a, void *) {
+  /* same block decomposition and per-block sums as the CUDA kernels (sequential inside a block) */
+  for (int blk = 0; blk < rrb_ppo_blocks(a.B); blk++) {
+    double s1 = 0.0, s2 = 0.0;
+    for (int b = blk * 128; b < a.B && b < (blk + 1) * 128; b++) {
+      double t1, t2;
+      rr_ppo_stage_a(a, b, t1, t2);
+      s1 += t1; s2 += t2;
+    }
+    a.adv_partial[2 * blk] = s1; a.adv_partial[2 * blk + 1] = s2;
+  }
+  double s1 = 0.0, s2 = 0.0;
+  for (int k = 0; k < a.nblkA; k++) { s1 += a.adv_partial[2 * k]; s2 += a.adv_partial[2 * k + 1]; }
+  const double n = (double)a.T * (double)a.B, mean = s1 / n;
+  double var = s2 / n - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const size_t N = (size_t)a.T * a.B;
+  for (int blk = 0; blk < rrb_ppo_blocks((int)N); blk++) {
+    float acc[3] = {0.f, 0.f, 0.f};
+    for (size_t i = (size_t)blk * 128; i < N && i < (size_t)(blk + 1) * 128; i++) {
+      float pol, val, ent;
+      rr_ppo_stage_b(a, i, (float)mean, (float)sqrt(var), pol, val, ent);
+      acc[0] += pol; acc[1] += val; acc[2] += ent;
+    }
+    for (int q = 0; q < 3; q++) a.loss_partial[3 * blk + q] = acc[q];
+  }
+  return 0;
+}
+
 #include "../../brax_rodent_run_b200/csrc/rr_api_impl.inl"

@@ -163,3 +163,53 @@ def test_graphed_update_matches_eager_update():
         assert abs(m_graph[k] - m_eager[k]) <= 1e-4 * max(1.0, abs(m_eager[k])), (k, m_graph[k], m_eager[k])
     assert float(d_eager.abs().max()) > 0.1 * cfg.learning_rate     # the update moved something
     assert float((d_graph - d_eager).abs().max()) < 0.05 * cfg.learning_rate, float((d_graph - d_eager).abs().max())
+
+
+def _loss_case(emu_or_cuda_env, device, seed=0, T=5, B=37):
+    """Random minibatch incl. terminations / truncations, a few saturated ratios and a large pre-softplus scale."""
+    from brax_rodent_run_b200.ppo import PPO, PPOConfig
+    cfg = PPOConfig(**dict(TINY, num_envs=emu_or_cuda_env.num_envs, tf32=False, cuda_graph=False))
+    agent = PPO(emu_or_cuda_env, cfg)
+    g = torch.Generator().manual_seed(seed)
+    A, obs = emu_or_cuda_env.action_size, emu_or_cuda_env.observation_size
+    r = lambda *s: torch.randn(*s, generator=g)
+    mb = dict(observation=r(T, B, obs), raw_action=1.5 * r(T, B, A), log_prob=-30 + 8 * r(T, B), reward=r(T, B),
+              discount=(torch.rand(T, B, generator=g) > 0.2).float(), truncation=(torch.rand(T, B, generator=g) > 0.9).float(),
+              next_observation_last=r(B, obs), entropy_noise=r(T, B, A))
+    mb["truncation"] = mb["truncation"] * (1 - mb["discount"])          # truncation only where the episode ended
+    mb = {k: v.to(device) for k, v in mb.items()}
+    with torch.no_grad():
+        agent.policy[-1].bias[A:A + 3] += 25.0                            # softplus threshold branch (> 20)
+    return agent, mb
+
+
+def _compare_fused_with_autograd(agent, mb, tol):
+    import dataclasses
+    outs = []
+    for fused in (False, True):
+        agent.cfg = dataclasses.replace(agent.cfg, fused_loss=fused)
+        for p in agent.params:
+            p.grad = None
+        total, metrics = agent.loss(mb)
+        total.backward()
+        outs.append((float(total), {k: float(v) for k, v in metrics.items()},
+                     torch.cat([p.grad.reshape(-1) for p in agent.params]).cpu()))
+    (t0, m0, g0), (t1, m1, g1) = outs
+    assert abs(t0 - t1) <= tol * max(1.0, abs(t0)), (t0, t1)
+    for k in m0:
+        assert abs(m0[k] - m1[k]) <= tol * max(1.0, abs(m0[k])), (k, m0[k], m1[k])
+    assert float(g0.abs().max()) > 0
+    assert float((g0 - g1).abs().max()) <= tol * float(g0.abs().max()), float((g0 - g1).abs().max())
+
+
+def test_fused_loss_matches_autograd_on_emulator(emu_lib):
+    agent, mb = _loss_case(tiny_env(emu_lib), "cpu")
+    _compare_fused_with_autograd(agent, mb, 2e-4)
+
+
+@pytest.mark.gpu
+def test_fused_loss_matches_autograd_on_gpu():
+    from brax_rodent_run_b200.env import Rodent
+    env = Rodent(synthetic_track(), num_envs=2, device="cuda:0", model=load_asset("rodent_0"), iterations=1, ls_iterations=1, n_frames=1)
+    agent, mb = _loss_case(env, "cuda:0", seed=1, T=10, B=512)
+    _compare_fused_with_autograd(agent, mb, 2e-4)
