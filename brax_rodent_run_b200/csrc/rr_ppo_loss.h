@@ -4,8 +4,8 @@
  * NormalTanhDistribution log-prob of the taken raw action, compute_gae, advantage normalisation, clipped surrogate, value
  * loss (0.5 * 0.5 * mse against vs), entropy of the tanh-normal estimated with one noise sample, and -- instead of
  * autograd over ~130 element-wise / reduction launches -- the analytic gradient w.r.t. logits and baseline.  Two stages:
- *   A  one environment column: log-prob per step, GAE scan over T, sum / sum of squares of the advantages
- *   B  one (t, env) element: losses and gradients
+ *   A  one environment column: GAE scan over T, sum / sum of squares of the advantages
+ *   B  one (t, env) element: log-prob, losses and gradients
  * The same text runs as two CUDA kernels (rr_api.cu) and as host loops in the test emulator (tests/emu/rr_emu.cpp).
  */
 #ifndef RR_PPO_LOSS_H_
@@ -43,19 +43,9 @@ struct RRPpoLossArgs {
 RR_PPO_HD float rr_softplus(float x) { return x > 20.f ? x : log1pf(expf(x)); } /* torch.nn.functional.softplus */
 RR_PPO_HD float rr_log_det_tanh(float x) { return 2.f * (RR_PPO_LOG2 - x - rr_softplus(-2.f * x)); }
 
-/* stage A for column b; returns (sum adv, sum adv^2) through s1 / s2 */
+/* stage A for column b: the GAE scan (sequential over T, nothing transcendental); returns (sum adv, sum adv^2) */
 RR_PPO_HD void rr_ppo_stage_a(const RRPpoLossArgs &a, int b, double &s1, double &s2) {
-  const int T = a.T, B = a.B, A = a.A;
-  for (int t = 0; t < T; t++) {
-    const size_t i = (size_t)t * B + b;
-    const float *lg = a.logits + i * 2 * A, *raw = a.raw_action + i * A;
-    float lp = 0.f;
-    for (int k = 0; k < A; k++) {
-      const float scale = rr_softplus(lg[A + k]) + 1e-3f, z = (raw[k] - lg[k]) / scale;
-      lp += -0.5f * z * z - logf(scale) - RR_PPO_HALF_LOG_2PI - rr_log_det_tanh(raw[k]);
-    }
-    a.lp[i] = lp;
-  }
+  const int T = a.T, B = a.B;
   float acc = 0.f, v_next = a.bootstrap[b], vs_next = a.bootstrap[b];
   s1 = 0.0; s2 = 0.0;
   for (int t = T - 1; t >= 0; t--) {
@@ -79,7 +69,14 @@ RR_PPO_HD void rr_ppo_stage_b(const RRPpoLossArgs &a, size_t i, float mean, floa
   const int A = a.A;
   const float invN = 1.f / ((float)a.T * (float)a.B);
   const float adv = a.normalize_advantage ? (a.adv[i] - mean) / (std_ + 1e-8f) : a.adv[i];
-  const float rho = expf(a.lp[i] - a.old_log_prob[i]);
+  const float *lg = a.logits + i * 2 * A, *raw = a.raw_action + i * A, *nz = a.noise + i * A;
+  float lp = 0.f; /* log-prob of the taken action under the current policy (first pass over the actions) */
+  for (int k = 0; k < A; k++) {
+    const float scale = rr_softplus(lg[A + k]) + 1e-3f, z = (raw[k] - lg[k]) / scale;
+    lp += -0.5f * z * z - logf(scale) - RR_PPO_HALF_LOG_2PI - rr_log_det_tanh(raw[k]);
+  }
+  a.lp[i] = lp;
+  const float rho = expf(lp - a.old_log_prob[i]);
   const float lo = 1.f - a.clip_eps, hi = 1.f + a.clip_eps;
   const float s1 = rho * adv, s2 = fminf(fmaxf(rho, lo), hi) * adv;
   pol = -fminf(s1, s2);
@@ -87,7 +84,6 @@ RR_PPO_HD void rr_ppo_stage_b(const RRPpoLossArgs &a, size_t i, float mean, floa
   const float d = a.vs[i] - a.baseline[i];
   val = 0.25f * d * d;
   a.grad_baseline[i] = -0.5f * d * invN;
-  const float *lg = a.logits + i * 2 * A, *raw = a.raw_action + i * A, *nz = a.noise + i * A;
   float *gl = a.grad_logits + i * 2 * A;
   const float ce = -a.entropy_cost * invN; /* d total / d entropy element */
   float e = 0.f;

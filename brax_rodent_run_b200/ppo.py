@@ -214,8 +214,12 @@ class PPO:
         assert env.num_envs == cfg.num_envs
         torch.manual_seed(cfg.seed)  # identical initial parameters on every rank
         obs, act = env.observation_size, env.action_size
-        self.policy = _mlp((obs,) + tuple(cfg.policy_hidden), 2 * act).to(self.device)
-        self.value = _mlp((obs,) + tuple(cfg.value_hidden), 1).to(self.device)
+        # The first layers take the observation zero-padded to a multiple of 16 features (1263 -> 1264): with an odd K the
+        # [5120 x 1263] x [1263 x 256] GEMMs fall to cuBLAS's unaligned kernels (3x slower).  The pad weights see only zeros:
+        # they get no gradient and are dropped by export_brax_params.
+        self._obs_dim, self._obs_pad = obs, (-obs) % 16 if self.device.type == "cuda" else 0
+        self.policy = _mlp((obs + self._obs_pad,) + tuple(cfg.policy_hidden), 2 * act).to(self.device)
+        self.value = _mlp((obs + self._obs_pad,) + tuple(cfg.value_hidden), 1).to(self.device)
         self.params = list(self.policy.parameters()) + list(self.value.parameters())
         self._use_graph = bool(cfg.cuda_graph) and self.device.type == "cuda"
         if self.device.type == "cuda" and cfg.tf32:
@@ -234,7 +238,12 @@ class PPO:
 
     # ---- acting -----------------------------------------------------------------------------------------------------
     def _norm(self, obs):
-        return self.normalizer.normalize(obs) if self.cfg.normalize_observations else obs
+        obs = self.normalizer.normalize(obs) if self.cfg.normalize_observations else obs
+        return F.pad(obs, (0, self._obs_pad)) if self._obs_pad else obs
+
+    def _norm_mb(self, obs):
+        """Observations of a minibatch: already normalised when they come out of training_step's batch."""
+        return obs if getattr(self, "_batch_is_normalized", False) else self._norm(obs)
 
     @torch.no_grad()
     def act(self, obs, deterministic=False):
@@ -264,19 +273,19 @@ class PPO:
     # ---- learning ---------------------------------------------------------------------------------------------------
     def loss(self, mb: Dict[str, torch.Tensor]):
         cfg = self.cfg
-        obs = self._norm(mb["observation"])                      # [T, b, obs]
+        obs = self._norm_mb(mb["observation"])                   # [T, b, obs]
         logits = self.policy(obs)
         baseline = self.value(obs).squeeze(-1)
         if cfg.fused_loss:
             with torch.no_grad():
-                bootstrap = self.value(self._norm(mb["next_observation_last"])).squeeze(-1)
+                bootstrap = self.value(self._norm_mb(mb["next_observation_last"])).squeeze(-1)
                 noise = mb.get("entropy_noise")
                 if noise is None:
                     noise = torch.randn(mb["raw_action"].shape, device=obs.device, generator=self.gen)
             total, policy_loss, v_loss, entropy_loss = _FusedPPOLoss.apply(logits, baseline, bootstrap, mb, noise, cfg, self.env._L)
             return total, dict(total_loss=total.detach(), policy_loss=policy_loss, v_loss=v_loss, entropy_loss=entropy_loss)
         with torch.no_grad():
-            bootstrap = self.value(self._norm(mb["next_observation_last"])).squeeze(-1)
+            bootstrap = self.value(self._norm_mb(mb["next_observation_last"])).squeeze(-1)
             rewards = mb["reward"] * cfg.reward_scaling
             truncation = mb["truncation"]
             termination = (1 - mb["discount"]) * (1 - truncation)
@@ -365,6 +374,10 @@ class PPO:
         data = {k: torch.cat([c[k] for c in chunks], dim=1 if k != "next_observation_last" else 0) for k in chunks[0]}
         if cfg.normalize_observations:
             self.normalizer.update(data["observation"], distributed=self.world > 1)
+        # the statistics are fixed for all epochs of this batch: normalise (and pad) it once instead of once per minibatch
+        data["observation"] = self._norm(data["observation"])
+        data["next_observation_last"] = self._norm(data["next_observation_last"])
+        self._batch_is_normalized = True
         nb = data["reward"].shape[1]
         metrics = {}
         for _ in range(cfg.num_updates_per_batch):
@@ -382,6 +395,7 @@ class PPO:
                 self.opt.step()
         if self._use_graph:
             metrics = {k: v.clone() for k, v in metrics.items()}
+        self._batch_is_normalized = False
         self.env_steps += n_unroll * cfg.unroll_length * cfg.num_envs * self.world
         return state, metrics
 
@@ -424,8 +438,8 @@ class PPO:
         """(normalizer, policy) in the flax naming brax pickles (`hidden_i` / kernel [in, out] / bias), as numpy."""
         def mlp(net):
             lin = [m for m in net if isinstance(m, nn.Linear)]
-            return {"params": {f"hidden_{i}": {"kernel": l.weight.detach().t().cpu().numpy(), "bias": l.bias.detach().cpu().numpy()}
-                               for i, l in enumerate(lin)}}
+            return {"params": {f"hidden_{i}": {"kernel": l.weight.detach().t()[:self._obs_dim if i == 0 else None].cpu().numpy(),
+                                               "bias": l.bias.detach().cpu().numpy()} for i, l in enumerate(lin)}}
         n = self.normalizer
         norm = dict(count=float(n.count), mean=n.mean.cpu().numpy(), summed_variance=n.summed_variance.cpu().numpy(),
                     std=n.std.cpu().numpy())
@@ -451,6 +465,8 @@ class PPO:
         with torch.no_grad():
             for i, l in enumerate(lin):
                 w, b = as_t(layers[f"hidden_{i}"]["kernel"]).t(), as_t(layers[f"hidden_{i}"]["bias"])
+                if i == 0 and self._obs_pad:
+                    w = F.pad(w, (0, self._obs_pad))
                 if w.shape != l.weight.shape:
                     raise ValueError(f"hidden_{i}: kernel {tuple(w.t().shape)} does not fit {tuple(l.weight.t().shape)}")
                 l.weight.copy_(w); l.bias.copy_(b)

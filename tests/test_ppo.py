@@ -137,6 +137,10 @@ def test_graphed_update_matches_eager_update():
         state, d = agent.unroll(state)
         chunks.append(d)
     data = {k: torch.cat([c[k] for c in chunks], dim=1 if k != "next_observation_last" else 0) for k in chunks[0]}
+    # as training_step: the batch is normalised once, the captured graph and the eager loss then take it as it is
+    data["observation"] = agent._norm(data["observation"])
+    data["next_observation_last"] = agent._norm(data["next_observation_last"])
+    agent._batch_is_normalized = True
     idx = torch.arange(3, 3 + cfg.batch_size, device="cuda:0")
     opt_tensors = [t for st in agent.opt.state.values() for t in st.values() if torch.is_tensor(t)]
     saved = [t.clone() for t in agent.params + opt_tensors]
@@ -173,6 +177,7 @@ def _loss_case(emu_or_cuda_env, device, seed=0, T=5, B=37):
     g = torch.Generator().manual_seed(seed)
     A, obs = emu_or_cuda_env.action_size, emu_or_cuda_env.observation_size
     r = lambda *s: torch.randn(*s, generator=g)
+    obs += agent._obs_pad
     mb = dict(observation=r(T, B, obs), raw_action=1.5 * r(T, B, A), log_prob=-30 + 8 * r(T, B), reward=r(T, B),
               discount=(torch.rand(T, B, generator=g) > 0.2).float(), truncation=(torch.rand(T, B, generator=g) > 0.9).float(),
               next_observation_last=r(B, obs), entropy_noise=r(T, B, A))
@@ -180,6 +185,7 @@ def _loss_case(emu_or_cuda_env, device, seed=0, T=5, B=37):
     mb = {k: v.to(device) for k, v in mb.items()}
     with torch.no_grad():
         agent.policy[-1].bias[A:A + 3] += 25.0                            # softplus threshold branch (> 20)
+    agent._batch_is_normalized = True                                     # the random "observations" go straight into the MLPs
     return agent, mb
 
 
