@@ -55,6 +55,19 @@
 #define RR_SYNC_LEVEL 3 /* 1: per substep; 2: + before each factorisation and the collision phase; 3: + per CG iteration;
                            4: + between the line search and the gradient update of an iteration */
 #endif
+#ifndef RR_SYNC_FACTOR
+#define RR_SYNC_FACTOR 1
+#endif
+#ifndef RR_SYNC_COLLIDE
+#define RR_SYNC_COLLIDE 1
+#endif
+#ifndef RR_SYNC_EULER
+#define RR_SYNC_EULER 0
+#endif
+#ifndef RR_SYNC_RNE
+#define RR_SYNC_RNE 0
+#endif
+#define RR_CTA_SYNC_IF(flag) do { if (flag) RR_CTA_SYNC(); } while (0)
 #define RR_CTA_SYNC_AT(level)                \
   do {                                       \
     if (RR_SYNC_LEVEL >= (level)) RR_CTA_SYNC(); \
@@ -1617,7 +1630,7 @@ RR_DEV void substep(Ctx<NS> &c, bool integrate, float &time) {
   if (c.last_substep) forward_outputs<NS>(c);
   dbg_copy<NS>(c, RR_DBG_M, c.M, m.nM);
   mul_m<NS>(c, c.ma_warm, c.warm); /* the only product with M the solver needs (see ctx_init) */
-  RR_CTA_SYNC_AT(2);
+  RR_CTA_SYNC_IF(RR_SYNC_LEVEL >= 2 && RR_SYNC_FACTOR);
   factor2<NS>(c, dt);
   for (int pass = 0; pass < 2; pass++) {
     float x[NS];
@@ -1631,7 +1644,7 @@ RR_DEV void substep(Ctx<NS> &c, bool integrate, float &time) {
       if (m.nefc == 0) {
         RR_FOR_S { c.qacc[s] = c.qacc_smooth[s]; c.qfrc_constraint[s] = 0.f; }
       } else {
-        RR_CTA_SYNC_AT(2);
+        RR_CTA_SYNC_IF(RR_SYNC_LEVEL >= 2 && RR_SYNC_COLLIDE);
         collision<NS>(c);
         prof<NS>(c, RR_PROF_COLLIDE);
         make_constraint<NS>(c);
@@ -1680,9 +1693,9 @@ template <int NS>
 RR_DEV void substep_idle(Ctx<NS> &c, bool integrate) {
   const RRModelDev &m = c.m;
   RR_CTA_SYNC_AT(1);
-  RR_CTA_SYNC_AT(2); /* before the factorisations */
+  RR_CTA_SYNC_IF(RR_SYNC_LEVEL >= 2 && RR_SYNC_FACTOR); /* before the factorisations */
   if (m.nefc != 0) {
-    RR_CTA_SYNC_AT(2); /* before the collision phase */
+    RR_CTA_SYNC_IF(RR_SYNC_LEVEL >= 2 && RR_SYNC_COLLIDE); /* before the collision phase */
 #pragma unroll 1
     for (int trip = 0; trip <= m.iterations; trip++) { RR_CTA_SYNC_AT(3); RR_CTA_SYNC_AT(4); }
   }
