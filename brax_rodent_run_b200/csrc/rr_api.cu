@@ -154,6 +154,11 @@ static int rrb_num_slots() {
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
   return (n_sm > 0 ? n_sm : 160) * RR_MAX_WPB;
 }
+static void *rrb_host_devptr(void *host) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
+}
 static int rrb_sync(void *stream) { return rrb_check(cudaStreamSynchronize((cudaStream_t)stream), "cudaStreamSynchronize"); }
 
 static int rrb_max_wpb(const RRModelDev &m) { return m.nv <= 96 ? RRMaxWpb<3>::value : RRMaxWpb<5>::value; }

@@ -106,8 +106,10 @@ int rr_env_init(rr_env *e, const rr_buffers *b, void *stream);
 /* Rodent.step (Rodent_Env_Brax.py:98-136): n_frames x mjx.step with ctrl = action, reward, done, metrics, obs
  * (+ the fused wrappers when enabled).  action: DEVICE [B, nu]. */
 int rr_env_step(rr_env *e, const rr_buffers *b, const float *action, int32_t n_frames, void *stream);
-/* Same step through HOST buffers: copies action host->device, runs the step, copies obs / reward / done back and
- * synchronises the stream.  This is the call the end-to-end benchmark times. */
+/* Same step through HOST buffers: copies action host->device, runs the step, brings obs / reward / done to the host and
+ * synchronises the stream.  When obs_host is pinned (device-accessible) memory the kernel stores the observation straight
+ * into it (zero-copy) and b->obs is not written; pageable memory gets a copy after the kernel.  This is the call the
+ * end-to-end benchmark times. */
 int rr_env_step_host(rr_env *e, const rr_buffers *b, const float *action_host, int32_t n_frames, float *obs_host,
                      float *reward_host, float *done_host, void *stream);
 

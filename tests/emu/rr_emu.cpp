@@ -135,6 +135,7 @@ static int rrb_malloc(void **p, size_t bytes) { *p = calloc(bytes ? bytes : 4, 1
 static void rrb_free(void *p) { free(p); }
 static int rrb_h2d(void *dst, const void *src, size_t bytes, void *) { memcpy(dst, src, bytes); return 0; }
 static int rrb_d2h(void *dst, const void *src, size_t bytes, void *) { memcpy(dst, src, bytes); return 0; }
+static void *rrb_host_devptr(void *) { return nullptr; }
 static int rrb_sync(void *) { return 0; }
 static int rrb_num_slots() { return 1; }
 static int rrb_geometry(const RRModelDev &, int B, int *ctas, int *wpb) { *ctas = B; *wpb = 1; return 0; }
