@@ -483,6 +483,10 @@ def train(environment: Rodent, cfg: PPOConfig, progress_fn: Callable[[int, Dict]
     per_eval = max(1, num_train // max(cfg.num_evals, 1))
     state = environment.reset(cfg.seed + agent.rank)
     metrics: Dict[str, float] = {}
+    if eval_env is not None and cfg.num_evals > 1:  # brax evaluates the untrained policy first (`num_evals` counts it)
+        m0 = agent.evaluate(eval_env)
+        if agent.rank == 0:
+            progress_fn(0, m0)
     t0 = time.time()
     for it in range(num_train):
         state, m = agent.training_step(state)

@@ -48,12 +48,15 @@ def main():
     ap.add_argument("--model", default="rodent_new")
     ap.add_argument("--clip", default="clips/84.p")
     ap.add_argument("--out", default="./model_checkpoints")
+    ap.add_argument("--eval-every", type=int, help="env steps between evaluations (config default: 5M)")
     a = ap.parse_args()
     config = dict(CONFIGS[a.config], env_name="rodent", algo_name="ppo", task_name="run")
     if a.num_timesteps:
         config["num_timesteps"] = a.num_timesteps
     if a.num_envs:
         config["num_envs"] = a.num_envs
+    if a.eval_every:
+        config["eval_every"] = a.eval_every
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
