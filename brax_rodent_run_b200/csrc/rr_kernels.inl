@@ -73,10 +73,6 @@
     if (RR_SYNC_LEVEL >= (level)) RR_CTA_SYNC(); \
   } while (0)
 
-/* unroll factor of the column loops of the triangular solves (code size vs. load pipelining) */
-#ifndef RR_SOLVE_UNROLL
-#define RR_SOLVE_UNROLL 8
-#endif
 /* 1: right-looking (scatter) L'DL (factor2_rl), 0: gather form (factor2).  Measured: 415 k vs 571 k env-steps/s -- the scatter
  * form moves every Schur-complement entry through shared memory twice per descendant; kept for the record only. */
 #ifndef RR_FACTOR_RL
