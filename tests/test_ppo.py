@@ -166,6 +166,16 @@ def test_graphed_update_matches_eager_update():
     for k in m_eager:
         assert abs(m_graph[k] - m_eager[k]) <= 1e-4 * max(1.0, abs(m_eager[k])), (k, m_graph[k], m_eager[k])
     assert float(d_eager.abs().max()) > 0.1 * cfg.learning_rate     # the update moved something
+    # the first layers are padded to a multiple of 16 input features on CUDA: the brax parameter exchange must hide that
+    import pickle
+    assert agent._obs_pad == (-env.observation_size) % 16 and agent.policy[0].in_features == env.observation_size + agent._obs_pad
+    norm, pol = agent.export_brax_params()
+    assert pol["params"]["hidden_0"]["kernel"].shape == (env.observation_size, 32)
+    other = PPO(env, PPOConfig(**{**cfg.__dict__, "seed": 9}))
+    other.import_brax_params(pickle.loads(pickle.dumps((norm, pol))))
+    a1, _, _ = agent.act(state.obs, deterministic=True)
+    a2, _, _ = other.act(state.obs, deterministic=True)
+    assert torch.allclose(a1, a2, atol=1e-5)
     assert float((d_graph - d_eager).abs().max()) < 0.05 * cfg.learning_rate, float((d_graph - d_eager).abs().max())
 
 
