@@ -52,14 +52,19 @@
 #define RR_MV_RECURRENCE 1
 #endif
 #ifndef RR_SYNC_LEVEL
-#define RR_SYNC_LEVEL 3 /* 1: per substep; 2: + before each factorisation and the collision phase; 3: + per CG iteration;
-                           4: + between the line search and the gradient update of an iteration */
+#define RR_SYNC_LEVEL 2 /* 1: per substep; 2: + before the factorisations (and the collision phase if RR_SYNC_COLLIDE);
+                           3: + per CG iteration; 4: + between the line search and the gradient update of an iteration.
+                           With the v15 code size (17 k instructions, I-cache hit rate 93 %) the per-substep rendezvous is
+                           what matters (none: 2.1x slower; every 2nd substep: -22 %); levels 1 / 2 / 3 / 4 run within 1 %. */
+#endif
+#ifndef RR_SYNC_PERIOD
+#define RR_SYNC_PERIOD 1 /* substep-start rendezvous every this many substeps */
 #endif
 #ifndef RR_SYNC_FACTOR
 #define RR_SYNC_FACTOR 1
 #endif
 #ifndef RR_SYNC_COLLIDE
-#define RR_SYNC_COLLIDE 1
+#define RR_SYNC_COLLIDE 0
 #endif
 #ifndef RR_SYNC_EULER
 #define RR_SYNC_EULER 0
@@ -1672,10 +1677,10 @@ RR_DEV void forward_outputs(Ctx<NS> &c) {
 /* One mjx.step: forward (B.1-B.7) then, if `integrate`, the implicit-damping Euler update (B.8).  The two
  * factorisations (M for the solver, M + dt diag(damping) for Euler) and their solves share one call site. */
 template <int NS>
-RR_DEV void substep(Ctx<NS> &c, bool integrate, float &time) {
+RR_DEV void substep(Ctx<NS> &c, bool integrate, float &time, int sub) {
   const RRModelDev &m = c.m;
   const float dt = m.timestep;
-  RR_CTA_SYNC_AT(1);
+  RR_CTA_SYNC_IF(RR_SYNC_LEVEL >= 1 && sub % RR_SYNC_PERIOD == 0);
   kinematics<NS>(c);
   prof<NS>(c, RR_PROF_FK);
   com_pos<NS>(c);
@@ -1762,9 +1767,9 @@ RR_DEV void substep(Ctx<NS> &c, bool integrate, float &time) {
 /* Padding pass of a persistent warp (its CTA has fewer environments than warps in this pass): run exactly the rendezvous
  * sequence of substep() / solve_constraints() and nothing else, so the live warps of the CTA get the issue slots. */
 template <int NS>
-RR_DEV void substep_idle(Ctx<NS> &c, bool integrate) {
+RR_DEV void substep_idle(Ctx<NS> &c, bool integrate, int sub) {
   const RRModelDev &m = c.m;
-  RR_CTA_SYNC_AT(1);
+  RR_CTA_SYNC_IF(RR_SYNC_LEVEL >= 1 && sub % RR_SYNC_PERIOD == 0);
   RR_CTA_SYNC_IF(RR_SYNC_LEVEL >= 2 && RR_SYNC_FACTOR); /* before the factorisations */
   if (m.nefc != 0) {
     RR_CTA_SYNC_IF(RR_SYNC_LEVEL >= 2 && RR_SYNC_COLLIDE); /* before the collision phase */
@@ -1806,12 +1811,12 @@ RR_DEV void env_run(const RRModelDev &m, const RRStepArgs &a, int env_in, int sl
   {
     const int nrun = a.mode == RR_MODE_INIT ? 1 : a.nsub;
     if (!c.live) {
-      for (int sub = 0; sub < nrun; sub++) substep_idle<NS>(c, a.mode != RR_MODE_INIT);
+      for (int sub = 0; sub < nrun; sub++) substep_idle<NS>(c, a.mode != RR_MODE_INIT, sub);
       return;
     }
     for (int sub = 0; sub < nrun; sub++) {
       c.last_substep = sub == nrun - 1;
-      substep<NS>(c, a.mode != RR_MODE_INIT, time);
+      substep<NS>(c, a.mode != RR_MODE_INIT, time, sub);
     }
   }
   __syncwarp();
