@@ -32,10 +32,10 @@ ENVS_PER_GPU = 4096
 N_FRAMES = 10
 ALGO_BYTES_PER_ENV_STEP = 7204  # state in/out + action + 1263-float obs + scalars
 FP32_PEAK_TFLOPS_NOMINAL = 148 * 128 * 2 * 1.965e9 / 1e12  # 74.4, no measured FP32 peak in MEASURED_PEAKS.json
-# dram__bytes_read.sum + dram__bytes_write.sum of one rr_step_kernel launch (profiles/r01_v15_ncu_raw.csv, `ncu --set full`):
-# 5.61 MB + 0.40 MB.  Below the algorithmic 29.5 MB because the 25 MB of state / observation written by a launch is still
+# dram__bytes_read.sum + dram__bytes_write.sum of one rr_step_kernel launch (profiles/r01_v17_ncu_raw.csv, `ncu --set full`):
+# 5.58 MB + 0.34 MB.  Below the algorithmic 29.5 MB because the 25 MB of state / observation written by a launch is still
 # resident in the 126 MB L2 when the kernel ends.
-NCU_DRAM_TRAFFIC_BYTES_PER_LAUNCH = 5_614_080 + 395_008
+NCU_DRAM_TRAFFIC_BYTES_PER_LAUNCH = 5_579_008 + 337_152
 
 
 def synthetic_track(n=250):
