@@ -1712,7 +1712,11 @@ RR_DEV void substep(Ctx<NS> &c, bool integrate, float &time, int sub) {
   for (int pass = 0; pass < 2; pass++) {
     float x[NS];
     RR_FOR_S x[s] = pass ? c.qfrc_smooth[s] + c.qfrc_constraint[s] : c.qfrc_smooth[s];
-    if (pass) solve_ld<NS>(c, x, c.M, c.dinv2); else solve_ld<NS>(c, x, c.LD, c.dinv);
+    {
+      float dv[NS]; /* one call site for both factors (code size) */
+      RR_FOR_S dv[s] = pass ? c.dinv2[s] : c.dinv[s];
+      solve_ld<NS>(c, x, pass ? c.M : c.LD, dv);
+    }
     prof<NS>(c, pass ? RR_PROF_EULER : RR_PROF_FACTOR);
     if (pass == 0) {
       dbg_copy<NS>(c, RR_DBG_LD, c.LD, m.nM);
