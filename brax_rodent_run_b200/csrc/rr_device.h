@@ -14,7 +14,7 @@
 
 /* integer tables: name, expression for the element count (informative) */
 #define RR_DEV_INT_TABLES(X)                                                                              \
-  X(body_parentid) X(body_eparent) X(body_rootslot) X(body_jntadr) X(body_jntnum) X(level_adr) X(level_body)              \
+  X(body_parentid) X(body_eparent) X(body_rootslot) X(body_jntadr) X(body_jntnum) X(body_anc) X(level_adr) X(level_body)              \
   X(jnt_type) X(jnt_qposadr) X(jnt_dofadr) X(jnt_bodyid)                                                  \
   X(dof_bodyid) X(dof_depth) X(dof_ndesc) X(dof_rowadr) X(dof_log2w) X(dof_pack) X(dof_cbmask) X(dof_descmask) X(dof_ancmask) X(M_meta)                            \
   X(act_dofadr) X(act_qposadr) X(act_dyntype) X(act_gaintype) X(act_biastype) X(act_ctrllimited)          \
@@ -52,6 +52,7 @@ struct RRSmem {
 
 struct RRModelDev {
   int nq, nv, nu, na, nbody, njnt, ngeom, nM, npair, ncon, nlimit, nefc, nlevel, nroot, ncb;
+  int nround; /* pointer-doubling rounds of the tree scans: 2^nround >= nlevel - 1; body_anc[k nbody + b] = 2^k-th effective ancestor (0 = world) */
   int solver, iterations, ls_iterations;
   float timestep, gravity[3], tolerance, ls_tolerance, impratio, meaninertia;
   RRSmem sm;
@@ -61,6 +62,7 @@ struct RRModelDev {
    * constant-bank load -- the solve loops index these once per column without touching the LSU.  Byte offsets (x 4) so that
    * a coefficient address is one add: krow4[i] = 4 rowadr[i], kdep4[i] = 4 depth[i].  Zero beyond nv. */
   int32_t krow4[160], kdep4[160];
+  uint8_t kpar[160]; /* body_parentid by value: the leaf-to-root accumulations read it from the constant bank (no LSU round trip in their serial chain) */
   const int32_t *ibuf;
   const float *fbuf;
   int ni, nf; /* element counts of ibuf / fbuf (multiples of 4) */

@@ -413,74 +413,112 @@ RR_DEV void dbg_vec(Ctx<NS> &c, int field, const float (&x)[NS]) {
 }
 
 /* ------------------------------------------------------------------------------------------ kinematics (B.1) */
+/* Tree scan by pointer doubling instead of a walk over the tree levels (27 dependent levels of quaternion algebra for the
+ * rodent, with 1 - 5 busy lanes each): every body first forms its transform RELATIVE to its effective parent (joint
+ * rotations included; all bodies in parallel), then nround = ceil(log2(depth)) rounds compose T_b <- T_anc_k(b) o T_b with
+ * anc_k = the 2^k-th ancestor (body_anc), all bodies per round in parallel, double-buffered between (xpos, xquat) and the
+ * LD array (dead until the factorisation).  World poses are identical to the level walk up to the association order of the
+ * products (1e-7 relative).  Joint anchors / axes are formed in the parent frame and mapped to the world afterwards. */
 template <int NS>
 RR_DEV void kinematics(Ctx<NS> &c) {
   const RRModelDev &m = c.m;
-  if (c.lane == 0) {
-    c.xpos[0] = c.xpos[1] = c.xpos[2] = 0.f;
-    c.xquat[0] = 1.f; c.xquat[1] = c.xquat[2] = c.xquat[3] = 0.f;
-    c.cinert[6] = c.cinert[7] = c.cinert[8] = 0.f; /* xipos of world (temp slot) */
-  }
+  const int nb = m.nbody, R = m.nround;
+  /* buffer 0 = (xpos, xquat); buffer 1 = LD as 8 floats per body (pos, -, quat).  Start so that round R ends in buffer 0. */
+  float *p_in = (R & 1) ? c.LD : c.xpos, *q_in = (R & 1) ? c.LD + 4 : c.xquat;
+  int sp_in = (R & 1) ? 8 : 3, sq_in = (R & 1) ? 8 : 4;
+  float *p_out = (R & 1) ? c.xpos : c.LD, *q_out = (R & 1) ? c.xquat : c.LD + 4;
+  int sp_out = (R & 1) ? 3 : 8, sq_out = (R & 1) ? 4 : 8;
   __syncwarp();
-  for (int lev = 1; lev < m.nlevel; lev++) {
-    int beg = RI(level_adr, lev), end = RI(level_adr, lev + 1);
-    for (int idx = beg + c.lane; idx < end; idx += 32) {
-      int b = RI(level_body, idx);
-      /* effective parent = nearest ancestor that carries joints (or the world); body_epos / body_equat are the fixed
-       * offsets of the jointless bodies in between composed on the host, so a chain of welded bodies costs one level */
-      int p = RI(body_eparent, b);
-      float ppos[3], pquat[4], bp[3], bq[4], pos[3], quat[4], r[3];
+  for (int b = c.lane; b < nb; b += 32) {
+    float pos[3], quat[4], r[3];
 #pragma unroll
-      for (int k = 0; k < 3; k++) { ppos[k] = c.xpos[3 * p + k]; bp[k] = RF(body_epos, 3 * b + k); }
+    for (int k = 0; k < 3; k++) pos[k] = RF(body_epos, 3 * b + k);
 #pragma unroll
-      for (int k = 0; k < 4; k++) { pquat[k] = c.xquat[4 * p + k]; bq[k] = RF(body_equat, 4 * b + k); }
-      rotq(r, bp, pquat);
+    for (int k = 0; k < 4; k++) quat[k] = RF(body_equat, 4 * b + k);
+    const int jadr = RI(body_jntadr, b), jnum = RI(body_jntnum, b);
+    for (int j = jadr; j < jadr + jnum; j++) {
+      const int qa = RI(jnt_qposadr, j), da = RI(jnt_dofadr, j);
+      if (RI(jnt_type, j) == RR_JNT_FREE) {
 #pragma unroll
-      for (int k = 0; k < 3; k++) pos[k] = ppos[k] + r[k];
-      quat_mul(quat, pquat, bq);
-      int jadr = RI(body_jntadr, b), jnum = RI(body_jntnum, b);
-      for (int j = jadr; j < jadr + jnum; j++) {
-        int qa = RI(jnt_qposadr, j), da = RI(jnt_dofadr, j);
-        if (RI(jnt_type, j) == RR_JNT_FREE) {
+        for (int k = 0; k < 3; k++) pos[k] = c.qpos[qa + k];
 #pragma unroll
-          for (int k = 0; k < 3; k++) pos[k] = c.qpos[qa + k];
+        for (int k = 0; k < 4; k++) quat[k] = c.qpos[qa + 3 + k];
+        normalize4(quat);
 #pragma unroll
-          for (int k = 0; k < 4; k++) quat[k] = c.qpos[qa + 3 + k];
-          normalize4(quat);
+        for (int k = 0; k < 4; k++) c.qpos[qa + 3 + k] = quat[k]; /* normalised quaternion is written back */
+      } else {
+        float jp[3], ja[3], anchor[3], axis[3], qloc[4], q2[4];
 #pragma unroll
-          for (int k = 0; k < 4; k++) c.qpos[qa + 3 + k] = quat[k]; /* normalised quaternion is written back */
-        } else {
-          float jp[3], ja[3], anchor[3], axis[3], qloc[4], q2[4];
+        for (int k = 0; k < 3; k++) { jp[k] = RF(jnt_pos, 3 * j + k); ja[k] = RF(jnt_axis, 3 * j + k); }
+        rotq(r, jp, quat);
 #pragma unroll
-          for (int k = 0; k < 3; k++) { jp[k] = RF(jnt_pos, 3 * j + k); ja[k] = RF(jnt_axis, 3 * j + k); }
-          rotq(r, jp, quat);
+        for (int k = 0; k < 3; k++) anchor[k] = r[k] + pos[k];
+        rotq(axis, ja, quat);
+        axis_angle_quat(qloc, ja, c.qpos[qa] - RF(qpos0, qa));
+        quat_mul(q2, quat, qloc);
 #pragma unroll
-          for (int k = 0; k < 3; k++) anchor[k] = r[k] + pos[k];
-          rotq(axis, ja, quat);
-          axis_angle_quat(qloc, ja, c.qpos[qa] - RF(qpos0, qa));
-          quat_mul(q2, quat, qloc);
+        for (int k = 0; k < 4; k++) quat[k] = q2[k];
+        rotq(r, jp, quat);
 #pragma unroll
-          for (int k = 0; k < 4; k++) quat[k] = q2[k];
-          rotq(r, jp, quat);
-#pragma unroll
-          for (int k = 0; k < 3; k++) {
-            pos[k] = anchor[k] - r[k];
-            c.cdof[6 * da + k] = axis[k];       /* temp: xaxis */
-            c.cdof[6 * da + 3 + k] = anchor[k]; /* temp: xanchor */
-          }
+        for (int k = 0; k < 3; k++) {
+          pos[k] = anchor[k] - r[k];
+          c.cdof[6 * da + k] = axis[k];       /* temp: joint axis, parent frame */
+          c.cdof[6 * da + 3 + k] = anchor[k]; /* temp: joint anchor, parent frame */
         }
       }
-      float ip[3];
+    }
+    if (b == 0) { pos[0] = pos[1] = pos[2] = 0.f; quat[0] = 1.f; quat[1] = quat[2] = quat[3] = 0.f; }
 #pragma unroll
-      for (int k = 0; k < 3; k++) { c.xpos[3 * b + k] = pos[k]; ip[k] = RF(body_ipos, 3 * b + k); }
+    for (int k = 0; k < 3; k++) p_in[sp_in * b + k] = pos[k];
 #pragma unroll
-      for (int k = 0; k < 4; k++) c.xquat[4 * b + k] = quat[k];
-      rotq(r, ip, quat);
+    for (int k = 0; k < 4; k++) q_in[sq_in * b + k] = quat[k];
+  }
+  __syncwarp();
+#pragma unroll 1
+  for (int rd = 0; rd < R; rd++) {
+    for (int b = c.lane; b < nb; b += 32) {
+      const int an = RI(body_anc, rd * nb + b);
+      float ap[3], aq[4], bp[3], bq[4], r[3], q2[4];
 #pragma unroll
-      for (int k = 0; k < 3; k++) c.cinert[10 * b + 6 + k] = pos[k] + r[k]; /* temp: xipos */
+      for (int k = 0; k < 3; k++) { ap[k] = p_in[sp_in * an + k]; bp[k] = p_in[sp_in * b + k]; }
+#pragma unroll
+      for (int k = 0; k < 4; k++) { aq[k] = q_in[sq_in * an + k]; bq[k] = q_in[sq_in * b + k]; }
+      rotq(r, bp, aq);
+      quat_mul(q2, aq, bq);
+#pragma unroll
+      for (int k = 0; k < 3; k++) p_out[sp_out * b + k] = ap[k] + r[k];
+#pragma unroll
+      for (int k = 0; k < 4; k++) q_out[sq_out * b + k] = q2[k];
     }
     __syncwarp();
+    { float *t = p_in; p_in = p_out; p_out = t; t = q_in; q_in = q_out; q_out = t; }
+    { int t = sp_in; sp_in = sp_out; sp_out = t; t = sq_in; sq_in = sq_out; sq_out = t; }
   }
+  /* world poses are now in (xpos, xquat): inertial-frame origins, then joint anchors / axes to the world */
+  for (int b = c.lane; b < nb; b += 32) {
+    float pos[3], quat[4], ip[3], r[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) { pos[k] = c.xpos[3 * b + k]; ip[k] = RF(body_ipos, 3 * b + k); }
+#pragma unroll
+    for (int k = 0; k < 4; k++) quat[k] = c.xquat[4 * b + k];
+    rotq(r, ip, quat);
+#pragma unroll
+    for (int k = 0; k < 3; k++) c.cinert[10 * b + 6 + k] = pos[k] + r[k]; /* temp: xipos */
+  }
+  for (int j = c.lane; j < m.njnt; j += 32) {
+    if (RI(jnt_type, j) == RR_JNT_FREE) continue;
+    const int da = RI(jnt_dofadr, j), p = RI(body_eparent, RI(jnt_bodyid, j));
+    float pp[3], pq[4], ax[3], an[3], r1[3], r2[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) { pp[k] = c.xpos[3 * p + k]; ax[k] = c.cdof[6 * da + k]; an[k] = c.cdof[6 * da + 3 + k]; }
+#pragma unroll
+    for (int k = 0; k < 4; k++) pq[k] = c.xquat[4 * p + k];
+    rotq(r1, ax, pq);
+    rotq(r2, an, pq);
+#pragma unroll
+    for (int k = 0; k < 3; k++) { c.cdof[6 * da + k] = r1[k]; c.cdof[6 * da + 3 + k] = pp[k] + r2[k]; } /* temp: xaxis, xanchor */
+  }
+  __syncwarp();
 }
 
 /* ------------------------------------------------------------------------------------------ com_pos (B.2) */
@@ -573,8 +611,9 @@ RR_DEV void crb_and_mass_matrix(Ctx<NS> &c) {
   for (int i = c.lane; i < 10 * m.nbody; i += 32) c.crb[i] = c.cinert[i];
   __syncwarp();
   /* lane q owns component q of every body: no cross-lane hazard, so no rendezvous inside the loop */
+#pragma unroll 4
   for (int b = m.nbody - 1; b > 0; b--) {
-    int p = RI(body_parentid, b);
+    const int p = m.kpar[b];
     if (c.lane < 10 && p > 0) c.crb[10 * p + c.lane] += c.crb[10 * b + c.lane];
   }
   __syncwarp();
@@ -908,60 +947,111 @@ RR_DEV void mul_m(Ctx<NS> &c, float (&y)[NS], const float (&v)[NS]) {
 }
 
 /* ------------------------------------------------------------------------------------------ velocity + rne (B.6) */
+/* The forward scans (cvel, cacc) are prefix SUMS over the chain of a body (everything is expressed about the tree COM, so no
+ * transforms are involved): like the kinematics they run by pointer doubling over body_anc instead of level by level.
+ *   A_b = sum over the joints of b of cdof qvel;  S = inclusive prefix of A;  the velocity entering b is S[eparent(b)];
+ *   the per-joint sequence of mjx com_vel (cdof_dot = cvel x cdof with the velocity accumulated so far) then runs per body
+ *   in parallel and leaves cvel_b and W_b = sum of cdof_dot qvel;  cacc_b = -gravity + inclusive prefix of W. */
+template <int NS>
+RR_DEV void tree_prefix6(Ctx<NS> &c, float *&in, float *&out) {
+  const RRModelDev &m = c.m;
+  const int nb = m.nbody;
+#pragma unroll 1
+  for (int rd = 0; rd < m.nround; rd++) {
+    for (int b = c.lane; b < nb; b += 32) {
+      const int an = RI(body_anc, rd * nb + b);
+      const float2 *ia = reinterpret_cast<const float2 *>(in + 6 * an), *ib = reinterpret_cast<const float2 *>(in + 6 * b);
+      float2 *ob = reinterpret_cast<float2 *>(out + 6 * b);
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        const float2 u = ia[k], v = ib[k];
+        ob[k] = make_float2(u.x + v.x, u.y + v.y);
+      }
+    }
+    __syncwarp();
+    float *t = in; in = out; out = t;
+  }
+}
+
 template <int NS>
 RR_DEV void com_vel_and_rne(Ctx<NS> &c, float (&qfrc_bias)[NS]) {
   const RRModelDev &m = c.m;
-  if (c.lane < 6) {
-    c.cvel[c.lane] = 0.f;
-    c.cacc[c.lane] = c.lane < 3 ? 0.f : -m.gravity[c.lane - 3];
+  const int nb = m.nbody;
+  const bool odd = m.nround & 1;
+  __syncwarp();
+  /* A_b -> the buffer from which nround swaps end in LD (so that cvel can be written while S is still being read) */
+  float *in = odd ? c.cvel : c.LD, *out = odd ? c.LD : c.cvel;
+  for (int b = c.lane; b < nb; b += 32) {
+    float av[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const int jadr = RI(body_jntadr, b), jnum = RI(body_jntnum, b);
+    for (int j = jadr; j < jadr + jnum; j++) {
+      const int d0 = RI(jnt_dofadr, j), nd = RI(jnt_type, j) == RR_JNT_FREE ? 6 : 1;
+      for (int d = 0; d < nd; d++) {
+        const float qv = c.qvel[d0 + d];
+#pragma unroll
+        for (int k = 0; k < 6; k++) av[k] += c.cdof[6 * (d0 + d) + k] * qv;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 6; k++) in[6 * b + k] = av[k];
   }
   __syncwarp();
-  for (int lev = 1; lev < m.nlevel; lev++) {
-    int beg = RI(level_adr, lev), end = RI(level_adr, lev + 1);
-    for (int idx = beg + c.lane; idx < end; idx += 32) {
-      int b = RI(level_body, idx);
-      int p = RI(body_eparent, b); /* jointless bodies in between add nothing to cvel / cacc */
-      float cv[6], ca[6];
+  tree_prefix6<NS>(c, in, out); /* `in` = LD now holds S */
+  float *win = c.cacc, *wout = c.LD; /* W_b starts in cacc (S in LD is still being read by the other lanes) */
+  const float *S = in;
+  for (int b = c.lane; b < nb; b += 32) {
+    const int p = RI(body_eparent, b);
+    float cv[6], w[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int k = 0; k < 6; k++) { cv[k] = c.cvel[6 * p + k]; ca[k] = c.cacc[6 * p + k]; }
-      int jadr = RI(body_jntadr, b), jnum = RI(body_jntnum, b);
-      for (int j = jadr; j < jadr + jnum; j++) {
-        int d0 = RI(jnt_dofadr, j);
-        if (RI(jnt_type, j) == RR_JNT_FREE) {
+    for (int k = 0; k < 6; k++) cv[k] = S[6 * p + k];
+    const int jadr = RI(body_jntadr, b), jnum = RI(body_jntnum, b);
+    for (int j = jadr; j < jadr + jnum; j++) {
+      const int d0 = RI(jnt_dofadr, j);
+      if (RI(jnt_type, j) == RR_JNT_FREE) {
 #pragma unroll
-          for (int d = 0; d < 3; d++) {
-            float qv = c.qvel[d0 + d];
+        for (int d = 0; d < 3; d++) {
+          const float qv = c.qvel[d0 + d];
 #pragma unroll
-            for (int k = 0; k < 6; k++) cv[k] += c.cdof[6 * (d0 + d) + k] * qv;
-          }
-          float cdd[3][6];
-#pragma unroll
-          for (int d = 0; d < 3; d++) {
-            float cd[6];
-#pragma unroll
-            for (int k = 0; k < 6; k++) cd[k] = c.cdof[6 * (d0 + 3 + d) + k];
-            motion_cross(cdd[d], cv, cd);
-          }
-#pragma unroll
-          for (int d = 0; d < 3; d++) {
-            float qv = c.qvel[d0 + 3 + d];
-#pragma unroll
-            for (int k = 0; k < 6; k++) { cv[k] += c.cdof[6 * (d0 + 3 + d) + k] * qv; ca[k] += cdd[d][k] * qv; }
-          }
-        } else {
-          float cd[6], cdd[6], qv = c.qvel[d0];
-#pragma unroll
-          for (int k = 0; k < 6; k++) cd[k] = c.cdof[6 * d0 + k];
-          motion_cross(cdd, cv, cd);
-#pragma unroll
-          for (int k = 0; k < 6; k++) { cv[k] += cd[k] * qv; ca[k] += cdd[k] * qv; }
+          for (int k = 0; k < 6; k++) cv[k] += c.cdof[6 * (d0 + d) + k] * qv;
         }
-      }
+        float cdd[3][6];
 #pragma unroll
-      for (int k = 0; k < 6; k++) { c.cvel[6 * b + k] = cv[k]; c.cacc[6 * b + k] = ca[k]; }
+        for (int d = 0; d < 3; d++) {
+          float cd[6];
+#pragma unroll
+          for (int k = 0; k < 6; k++) cd[k] = c.cdof[6 * (d0 + 3 + d) + k];
+          motion_cross(cdd[d], cv, cd);
+        }
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+          const float qv = c.qvel[d0 + 3 + d];
+#pragma unroll
+          for (int k = 0; k < 6; k++) { cv[k] += c.cdof[6 * (d0 + 3 + d) + k] * qv; w[k] += cdd[d][k] * qv; }
+        }
+      } else {
+        float cd[6], cdd[6];
+        const float qv = c.qvel[d0];
+#pragma unroll
+        for (int k = 0; k < 6; k++) cd[k] = c.cdof[6 * d0 + k];
+        motion_cross(cdd, cv, cd);
+#pragma unroll
+        for (int k = 0; k < 6; k++) { cv[k] += cd[k] * qv; w[k] += cdd[k] * qv; }
+      }
     }
-    __syncwarp();
+    if (b == 0) {
+#pragma unroll
+      for (int k = 0; k < 6; k++) cv[k] = 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 6; k++) { c.cvel[6 * b + k] = cv[k]; win[6 * b + k] = w[k]; }
   }
+  __syncwarp();
+  tree_prefix6<NS>(c, win, wout); /* `win` (cacc or LD) now holds the inclusive prefix of W */
+  for (int i = c.lane; i < 6 * nb; i += 32) {
+    const int k = i % 6;
+    c.cacc[i] = win[i] - (k >= 3 ? m.gravity[k - 3] : 0.f);
+  }
+  __syncwarp();
   /* local body forces */
   for (int b = c.lane; b < m.nbody; b += 32) {
     float ci[10], cv[6], ca[6], f1[6], f2[6], f3[6];
@@ -976,8 +1066,9 @@ RR_DEV void com_vel_and_rne(Ctx<NS> &c, float (&qfrc_bias)[NS]) {
     for (int k = 0; k < 6; k++) c.cfrc[6 * b + k] = f1[k] + f3[k]; /* cfrc aliases cacc: body-local, in place */
   }
   __syncwarp();
+#pragma unroll 4
   for (int b = m.nbody - 1; b > 0; b--) { /* lane q owns component q: no rendezvous needed inside the loop */
-    int p = RI(body_parentid, b);
+    const int p = m.kpar[b];
     if (c.lane < 6 && p > 0) c.cfrc[6 * p + c.lane] += c.cfrc[6 * b + c.lane];
   }
   __syncwarp();

@@ -79,6 +79,7 @@ inline void rr_host_model_build(RRHostModel &hm, const int32_t *dir, const int32
   d.impratio = (float)of[RR_OF_IMPRATIO]; d.meaninertia = (float)of[RR_OF_MEANINERTIA];
   const int nq = d.nq, nv = d.nv, nu = d.nu, nb = d.nbody, nj = d.njnt, nM = d.nM, np = d.npair, nc = d.ncon, nl = d.nlimit;
   if (nv > 160) throw std::runtime_error("NotImplemented: nv > 160");
+  if (nb > 160) throw std::runtime_error("NotImplemented: nbody > 160");
   if (d.na != nu && d.na != 0) {
     /* mixed stateful / stateless actuators are fine; nothing to check */
   }
@@ -153,6 +154,24 @@ inline void rr_host_model_build(RRHostModel &hm, const int32_t *dir, const int32
   t_level_adr[0] = 0;
   t_level_adr[d.nlevel] = (int)t_level_body.size();
   if (t_level_body.empty()) t_level_body.push_back(0);
+  /* pointer-doubling tables for the tree scans (kinematics, com_vel): the 2^k-th effective ancestor of every body.
+   * A free-joint body takes its pose from qpos whatever its parent is, so it hangs off the world here. */
+  {
+    const int32_t *jadr0 = B.I(RR_FID(body_jntadr)), *jnum0 = B.I(RR_FID(body_jntnum)), *jtype0 = B.I(RR_FID(jnt_type));
+    for (int b = 1; b < nb; b++)
+      for (int j = jadr0[b]; j < jadr0[b] + jnum0[b]; j++)
+        if (jtype0[j] == RR_JNT_FREE) {
+          if (t_body_eparent[b] != 0) throw std::runtime_error("NotImplemented: free joint below a moving body");
+          if (jnum0[b] != 1) throw std::runtime_error("NotImplemented: free joint sharing a body with other joints");
+        }
+    int R = 0;
+    while ((1 << R) < maxd) R++;
+    d.nround = R;
+    t_body_anc.assign((size_t)std::max(R, 1) * nb, 0);
+    for (int b = 0; b < nb; b++) t_body_anc[b] = t_body_eparent[b];
+    for (int k = 1; k < R; k++)
+      for (int b = 0; b < nb; b++) t_body_anc[(size_t)k * nb + b] = t_body_anc[(size_t)(k - 1) * nb + t_body_anc[(size_t)(k - 1) * nb + b]];
+  }
 
   /* ---- joints ---- */
   cpI(t_jnt_type, RR_FID(jnt_type)); cpI(t_jnt_qposadr, RR_FID(jnt_qposadr)); cpI(t_jnt_dofadr, RR_FID(jnt_dofadr));
@@ -195,6 +214,7 @@ inline void rr_host_model_build(RRHostModel &hm, const int32_t *dir, const int32
   t_dof_pack.resize(nv);
   for (int i = 0; i < nv; i++) t_dof_pack[i] = t_dof_rowadr[i] | (t_dof_depth[i] << 16) | (t_dof_ndesc[i] << 24);
   for (int i = 0; i < 160; i++) { d.krow4[i] = i < nv ? 4 * t_dof_rowadr[i] : 0; d.kdep4[i] = i < nv ? 4 * t_dof_depth[i] : 0; }
+  for (int b = 0; b < 160; b++) d.kpar[b] = (uint8_t)(b < nb ? parent[b] : 0);
   /* per dof and block of 32 columns: which columns are descendants / ancestors of the dof (the solves' predicates) */
   {
     const int nb32 = (nv + 31) / 32;
@@ -357,7 +377,7 @@ inline void rr_host_model_build(RRHostModel &hm, const int32_t *dir, const int32
   auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };
   s.qpos = take(nq); s.qvel = take(nv); s.act = take(d.na); s.ctrl = take(nu); s.actdot = take(d.na);
   s.com = take(3 * d.nroot); s.vbuf = take(nv);  s.xq1 = take(4); s.prof_acc = take(16);
-  s.M = take(nM); s.LD = take(nM);
+  s.M = take(nM); s.LD = take(std::max(nM, 8 * nb)); /* LD doubles as the second buffer of the tree scans (8 floats per body) */
   s.xpos = take(3 * nb); s.xquat = take(4 * nb); s.cdof = take(6 * nv);
   const int c0 = o;
   /* C1 */
