@@ -21,9 +21,9 @@ _LIBS = {}
 def build(force: bool = False) -> None:
     """Compile librr_oracle_{f32,f64}.so with gcc (no-op when up to date)."""
     src = os.path.join(_HERE, "rr_oracle.c")
-    outs = [os.path.join(_HERE, f"librr_oracle_{p}.so") for p in ("f32", "f64")]
+    outs = [os.path.join(_HERE, f"librr_oracle_{p}.so") for p in ("f32", "f64", "cnt")]
     hdr = os.path.join(_HERE, "..", "include", "rr_model_fields.h")
-    newest = max(os.path.getmtime(src), os.path.getmtime(hdr))
+    newest = max(os.path.getmtime(p) for p in (src, hdr, os.path.join(_HERE, "rr_oracle_count.cpp"), os.path.join(_HERE, "rr_opcount.hpp")))
     if not force and all(os.path.exists(o) and os.path.getmtime(o) >= newest for o in outs):
         return
     subprocess.check_call(["make", "-C", _HERE, "-B", "all"], stdout=subprocess.DEVNULL)
@@ -50,6 +50,9 @@ def _lib(precision: str):
         L.rro_scalar.restype = ctypes.c_double
         L.rro_scalar.argtypes = [vp, ctypes.c_char_p]
         L.rro_set_time.argtypes = [vp, ctypes.c_double]
+        if precision == "cnt":
+            L.rro_ops_total.restype = ctypes.c_longlong
+            L.rro_ops_useful.restype = ctypes.c_longlong
         _LIBS[precision] = L
     return _LIBS[precision]
 
@@ -94,6 +97,13 @@ class Oracle:
 
     def forward(self):
         self._L.rro_forward(self._h)
+
+    def ops(self, reset: bool = False):
+        """(total, useful) floating-point operations executed so far (precision "cnt" only; rr_oracle_count.cpp)."""
+        r = (int(self._L.rro_ops_total()), int(self._L.rro_ops_useful()))
+        if reset:
+            self._L.rro_ops_reset()
+        return r
 
     def step(self, n: int = 1):
         self._L.rro_step_n(self._h, n)
