@@ -128,7 +128,8 @@ extern "C" int rr_debug_field(const rr_model *m, const char *name, int32_t *offs
 
 static const char *const kProfNames[RR_NPROF] = {"load", "kinematics", "com_pos", "solver_cost_JTf", "mass_matrix", "factor", "solver_Minv_grad",
                                                   "rne", "smooth", "collision", "make_constraint", "solver_init",
-                                                  "solver_linesearch", "solver_update", "euler", "epilogue"};
+                                                  "solver_linesearch", "solver_update", "euler", "epilogue",
+                                                  "wait_substep", "wait_factor", "mul_m_warm", "factor2", "ls_pre", "ls_mul_j", "ls_eval_first2", "ls_loop", "solver_cost"};
 extern "C" int rr_prof_count(void) { return RR_NPROF; }
 extern "C" const char *rr_prof_name(int32_t i) { return (i >= 0 && i < RR_NPROF) ? kProfNames[i] : ""; }
 

@@ -116,7 +116,9 @@ struct RRStepArgs {
 enum {
   RR_PROF_LOAD = 0, RR_PROF_FK, RR_PROF_COM, RR_PROF_CRB, RR_PROF_QM, RR_PROF_FACTOR, RR_PROF_VEL, RR_PROF_RNE,
   RR_PROF_SMOOTH, RR_PROF_COLLIDE, RR_PROF_CONSTRAINT, RR_PROF_SOLVE_INIT, RR_PROF_SOLVE_LS, RR_PROF_SOLVE_UPD,
-  RR_PROF_EULER, RR_PROF_EPILOGUE, RR_NPROF
+  RR_PROF_EULER, RR_PROF_EPILOGUE,
+  RR_PROF_WAIT, RR_PROF_WAIT2, RR_PROF_MULM, RR_PROF_FACTOR2, RR_PROF_LS_PRE, RR_PROF_LS_MULJ, RR_PROF_LS_EVAL2, RR_PROF_LS_LOOP, RR_PROF_COST,
+  RR_NPROF
 };
 
 #endif /* RR_DEVICE_H_ */

@@ -653,101 +653,111 @@ RR_DEV void crb_and_mass_matrix(Ctx<NS> &c) {
 template <int NS>
 RR_DEV void factor2(Ctx<NS> &c, float dt) {
   const RRModelDev &m = c.m;
-  float4 *stage = reinterpret_cast<float4 *>(c.cinert); /* per descendant (w_j, w2_j, rowadr_j, -) [x2 in paired steps]: up to
-                                                          8 (nv - 1) floats <= 10 nbody; cinert is dead here (its
-                                                          observation slice was stored by forward_outputs) */
+  /* staging, per descendant j of the step's rows: w = L(j, row) D_j for up to 4 rows x 2 matrices (two float4) and the row
+   * address of j.  The C1 region (cinert .. cfrc) is dead here: its observation slices were stored by forward_outputs. */
+  const int nd4 = (m.nv + 3) & ~3;
+  float4 *stA = reinterpret_cast<float4 *>(c.cinert), *stB = stA + nd4;
+  int *stR = reinterpret_cast<int *>(c.cinert + 8 * nd4);
   float *LD = c.LD, *L2 = c.M;
   __syncwarp();
 #pragma unroll 1
   for (int k = m.nv - 1; k >= 0;) {
     const int pk = RI(dof_pack, k); /* rowadr | depth << 16 | ndesc << 24 */
     const int adr = pk & 0xffff, mk = (pk >> 16) & 255, nd = (int)((unsigned)pk >> 24);
-    const float damp = dt * RF(dof_damping, k);
-    const int lwp = RI(dof_log2w, k); /* bits 0-7: log2 of the row width rounded up; bit 8: row k - 1 can ride along */
-    if (lwp & 256) {
-      /* Two rows per step.  k - 1 is the parent of k and has no other child, so its descendants are those of k plus k
-       * itself: both rows run over the same descendant rows (loaded once) and row k's own contribution to row k - 1 is
-       * applied from registers.  Halves the number of dependent steps along a chain. */
-      const int kp = k - 1, adrp = RI(dof_rowadr, kp);
-      const float dampp = dt * RF(dof_damping, kp);
-      const int lw = lwp & 255, W = 1 << lw, G = 32 >> lw;
-      const int s0 = c.lane & (W - 1), g = c.lane >> lw;
-      const bool onA = s0 <= mk, onB = s0 < mk; /* row k has mk + 1 entries, row k - 1 has mk */
-      const int soA = onA ? s0 : 0, soB = onB ? s0 : 0;
-      if (nd > 0) {
-        for (int jj = c.lane; jj < nd; jj += 32) {
-          const int pj = RI(dof_pack, k + 1 + jj), rj = pj & 0xffff, dj = (pj >> 16) & 255;
-          const float D1 = LD[rj + dj], D2 = L2[rj + dj];
-          stage[2 * jj] = make_float4(LD[rj + mk] * D1, L2[rj + mk] * D2, __int_as_float(rj), 0.f);
-          stage[2 * jj + 1] = make_float4(LD[rj + mk - 1] * D1, L2[rj + mk - 1] * D2, 0.f, 0.f);
-        }
-      }
-      float a1 = (g == 0 && onA) ? L2[adr + soA] : 0.f, a2 = a1;   /* row k:     LD / L2 accumulators */
-      float b1 = (g == 0 && onB) ? L2[adrp + soB] : 0.f, b2 = b1;  /* row k - 1 */
-      if (g == 0 && s0 == mk) a2 += damp;
-      if (g == 0 && s0 == mk - 1) b2 += dampp;
-      __syncwarp();
-#pragma unroll 2
-      for (int jj = g; jj < nd; jj += G) {
-        const float4 wa = stage[2 * jj], wb = stage[2 * jj + 1];
-        const int rj = __float_as_int(wa.z);
-        const float l1 = onA ? LD[rj + soA] : 0.f, l2 = onA ? L2[rj + soA] : 0.f;
-        a1 -= wa.x * l1; a2 -= wa.y * l2;
-        b1 -= onB ? wb.x * l1 : 0.f; b2 -= onB ? wb.y * l2 : 0.f;
-      }
-      for (int o = W; o < 32; o <<= 1) {
-        a1 += __shfl_xor_sync(RR_FULL, a1, o); a2 += __shfl_xor_sync(RR_FULL, a2, o);
-        b1 += __shfl_xor_sync(RR_FULL, b1, o); b2 += __shfl_xor_sync(RR_FULL, b2, o);
-      }
-      /* finish row k, fold it into row k - 1, finish row k - 1 */
-      const float dA1 = __shfl_sync(RR_FULL, a1, mk), dA2 = __shfl_sync(RR_FULL, a2, mk);
-      const float wk1 = __shfl_sync(RR_FULL, a1, mk - 1), wk2 = __shfl_sync(RR_FULL, a2, mk - 1); /* L(k, k-1) D_k */
-      const float iA1 = RR_RCP(dA1), iA2 = RR_RCP(dA2);
-      const float lA1 = a1 * iA1, lA2 = a2 * iA2;
-      b1 -= onB ? wk1 * lA1 : 0.f;
-      b2 -= onB ? wk2 * lA2 : 0.f;
-      const float dB1 = __shfl_sync(RR_FULL, b1, mk - 1), dB2 = __shfl_sync(RR_FULL, b2, mk - 1);
-      const float iB1 = RR_RCP(dB1), iB2 = RR_RCP(dB2);
-      if (g == 0 && s0 < mk) { LD[adr + s0] = lA1; L2[adr + s0] = lA2; }
-      if (g == 0 && s0 < mk - 1) { LD[adrp + s0] = b1 * iB1; L2[adrp + s0] = b2 * iB2; }
-      if (c.lane == 0) { LD[adr + mk] = dA1; L2[adr + mk] = dA2; LD[adrp + mk - 1] = dB1; L2[adrp + mk - 1] = dB2; }
-      __syncwarp();
-      k -= 2;
-      continue;
-    }
-    if (nd > 0) {
-      for (int jj = c.lane; jj < nd; jj += 32) {
-        const int pj = RI(dof_pack, k + 1 + jj), rj = pj & 0xffff, dj = (pj >> 16) & 255;
-        stage[jj] = make_float4(LD[rj + mk] * LD[rj + dj], L2[rj + mk] * L2[rj + dj], __int_as_float(rj), 0.f);
-      }
-    }
+    const int lwp = RI(dof_log2w, k); /* bits 0-7: log2 of the row width rounded up; bits 8-9: rows k-1 .. k-T+1 ride along */
     if (mk < 32) {
-      /* short rows leave lanes idle: split the descendants over G = 32 / W lane groups (W = row width rounded up to a
-       * power of two) and add the partial sums with shuffles */
+      /* Up to four rows per step.  k-1 .. k-T+1 are the successive parents of k along a chain without other children, so
+       * their descendants are those of k plus the rows of the step itself: all rows run over the same descendant rows
+       * (loaded once) and the contribution of a finished row to the remaining ones is applied from registers.  Short rows
+       * leave lanes idle: the descendants are split over G = 32 / W lane groups (W = width of row k rounded up to a power
+       * of two) and the partial sums added with shuffles. */
+      const int T = ((lwp >> 8) & 3) + 1;
       const int lw = lwp & 255, W = 1 << lw, G = 32 >> lw;
       const int s0 = c.lane & (W - 1), g = c.lane >> lw;
       const bool on = s0 <= mk;
       const int so = on ? s0 : 0;
-      float acc = (g == 0 && on) ? L2[adr + so] : 0.f, acc2 = acc;
-      if (g == 0 && s0 == mk) acc2 += damp;
+      int adr_r[4];
+      float acc[4][2];
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        const int kr = k - r < 0 ? 0 : k - r;
+        adr_r[r] = m.krow4[kr] >> 2;
+        const bool mine = r < T && g == 0 && s0 <= mk - r;
+        const float v = mine ? L2[adr_r[r] + (mine ? s0 : 0)] : 0.f;
+        acc[r][0] = v;
+        acc[r][1] = v + ((mine && s0 == mk - r) ? dt * RF(dof_damping, kr) : 0.f);
+      }
+      for (int jj = c.lane; jj < nd; jj += 32) {
+        const int pj = RI(dof_pack, k + 1 + jj), rj = pj & 0xffff, dj = (pj >> 16) & 255;
+        const float D1 = LD[rj + dj], D2 = L2[rj + dj];
+        float w[4][2];
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+          const int e = rj + (r < T ? mk - r : mk);
+          w[r][0] = r < T ? LD[e] * D1 : 0.f;
+          w[r][1] = r < T ? L2[e] * D2 : 0.f;
+        }
+        stA[jj] = make_float4(w[0][0], w[0][1], w[1][0], w[1][1]);
+        if (T > 2) stB[jj] = make_float4(w[2][0], w[2][1], w[3][0], w[3][1]);
+        stR[jj] = rj;
+      }
       __syncwarp();
+      if (T > 2) {
+#pragma unroll 2
+        for (int jj = g; jj < nd; jj += G) {
+          const float4 wa = stA[jj], wb = stB[jj];
+          const int rj = stR[jj];
+          const float l1 = on ? LD[rj + so] : 0.f, l2 = on ? L2[rj + so] : 0.f;
+          acc[0][0] -= wa.x * l1; acc[0][1] -= wa.y * l2; acc[1][0] -= wa.z * l1; acc[1][1] -= wa.w * l2;
+          acc[2][0] -= wb.x * l1; acc[2][1] -= wb.y * l2; acc[3][0] -= wb.z * l1; acc[3][1] -= wb.w * l2;
+        }
+      } else {
 #pragma unroll 4
-      for (int jj = g; jj < nd; jj += G) {
-        const float4 wr = stage[jj];
-        const int rj = __float_as_int(wr.z);
-        acc -= on ? wr.x * LD[rj + so] : 0.f;
-        acc2 -= on ? wr.y * L2[rj + so] : 0.f;
+        for (int jj = g; jj < nd; jj += G) {
+          const float4 wa = stA[jj];
+          const int rj = stR[jj];
+          const float l1 = on ? LD[rj + so] : 0.f, l2 = on ? L2[rj + so] : 0.f;
+          acc[0][0] -= wa.x * l1; acc[0][1] -= wa.y * l2; acc[1][0] -= wa.z * l1; acc[1][1] -= wa.w * l2;
+        }
       }
       for (int o = W; o < 32; o <<= 1) {
-        acc += __shfl_xor_sync(RR_FULL, acc, o);
-        acc2 += __shfl_xor_sync(RR_FULL, acc2, o);
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+          if (r < T) {
+            acc[r][0] += __shfl_xor_sync(RR_FULL, acc[r][0], o);
+            acc[r][1] += __shfl_xor_sync(RR_FULL, acc[r][1], o);
+          }
+        }
       }
-      const float dk = __shfl_sync(RR_FULL, acc, mk), dk2 = __shfl_sync(RR_FULL, acc2, mk);
-      const float inv = RR_RCP(dk), inv2 = RR_RCP(dk2);
-      if (g == 0 && s0 < mk) { LD[adr + s0] = acc * inv; L2[adr + s0] = acc2 * inv2; }
-      if (c.lane == 0) { LD[adr + mk] = dk; L2[adr + mk] = dk2; }
-    } else {
-      /* rows of 33 .. 64 entries: two registers per lane and matrix */
+      /* finish the rows leaf-most first; each finished row is folded into the ones above it */
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        if (r < T) {
+          const int dg = mk - r; /* diagonal position of row k - r */
+          const float d1 = __shfl_sync(RR_FULL, acc[r][0], dg), d2 = __shfl_sync(RR_FULL, acc[r][1], dg);
+          const float l1 = acc[r][0] * RR_RCP(d1), l2 = acc[r][1] * RR_RCP(d2);
+#pragma unroll
+          for (int q = r + 1; q < 4; q++) {
+            if (q < T) {
+              const float u1 = __shfl_sync(RR_FULL, acc[r][0], mk - q), u2 = __shfl_sync(RR_FULL, acc[r][1], mk - q);
+              acc[q][0] -= u1 * l1; acc[q][1] -= u2 * l2;
+            }
+          }
+          if (g == 0 && s0 < dg) { LD[adr_r[r] + s0] = l1; L2[adr_r[r] + s0] = l2; }
+          if (c.lane == 0) { LD[adr_r[r] + dg] = d1; L2[adr_r[r] + dg] = d2; }
+        }
+      }
+      __syncwarp();
+      k -= T;
+      continue;
+    }
+    /* rows of 33 .. 64 entries: two registers per lane and matrix, one row per step */
+    const float damp = dt * RF(dof_damping, k);
+    for (int jj = c.lane; jj < nd; jj += 32) {
+      const int pj = RI(dof_pack, k + 1 + jj), rj = pj & 0xffff, dj = (pj >> 16) & 255;
+      stA[jj] = make_float4(LD[rj + mk] * LD[rj + dj], L2[rj + mk] * L2[rj + dj], __int_as_float(rj), 0.f);
+    }
+    {
       const int s0 = c.lane, s1 = c.lane + 32;
       const bool on1 = s1 <= mk;
       const int so1 = on1 ? s1 : 0;
@@ -756,7 +766,7 @@ RR_DEV void factor2(Ctx<NS> &c, float dt) {
       __syncwarp();
 #pragma unroll 2
       for (int jj = 0; jj < nd; jj++) {
-        const float4 wr = stage[jj];
+        const float4 wr = stA[jj];
         const int rj = __float_as_int(wr.z);
         a0 -= wr.x * LD[rj + s0];
         b0 -= wr.y * L2[rj + s0];
@@ -1535,6 +1545,39 @@ RR_DEV void ls_eval(Ctx<NS> &c, int nra, const float (&alpha)[NA], float g0, flo
   }
 }
 
+/* The three candidates of a line-search iteration, one per GROUP OF 8 LANES (the fourth group idles): a group walks all
+ * active rows with stride 8 for its own step size, so the reduction is 3 sums over 8 lanes (9 shuffles in 3 dependent rounds)
+ * plus one round that hands every lane the three finished points, instead of 9 sums over 32 lanes (45 shuffles in 5 rounds).
+ * The line search is the longest serial chain of a solver iteration, and shuffles share the one-per-clock LSU port of the SM
+ * with every other warp of the CTA. */
+template <int NS>
+RR_DEV void ls_eval3(Ctx<NS> &c, int nra, const float (&alpha)[3], float g0, float g1, float g2, LSPoint (&out)[3]) {
+  const int grp = c.lane >> 3, sub = c.lane & 7;
+  const float al = grp == 0 ? alpha[0] : (grp == 1 ? alpha[1] : alpha[2]);
+  float q0 = 0.f, q1 = 0.f, q2 = 0.f;
+#pragma unroll 2
+  for (int r = sub; r < nra; r += 8) {
+    const float ja = c.row_Jaref[r], jv = c.row_jv[r], D = c.row_D[r];
+    const float jaD = ja * D, jvD = jv * D;
+    if (ja + al * jv < 0.f) { q0 += 0.5f * ja * jaD; q1 += jv * jaD; q2 += 0.5f * jv * jvD; }
+  }
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) {
+    q0 += __shfl_xor_sync(RR_FULL, q0, o);
+    q1 += __shfl_xor_sync(RR_FULL, q1, o);
+    q2 += __shfl_xor_sync(RR_FULL, q2, o);
+  }
+  q0 += g0; q1 += g1; q2 += g2;
+  const float cost = al * al * q2 + al * q1 + q0, d0 = 2.f * al * q2 + q1, d1 = 2.f * q2 + (q2 == 0.f ? RR_MINVAL : 0.f);
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    out[k].alpha = alpha[k];
+    out[k].cost = __shfl_sync(RR_FULL, cost, 8 * k);
+    out[k].d0 = __shfl_sync(RR_FULL, d0, 8 * k);
+    out[k].d1 = __shfl_sync(RR_FULL, d1, 8 * k);
+  }
+}
+
 /* Given qacc (regs): Jaref = J qacc - aref (rows, smem).  Ma = M qacc comes from the caller: M qacc_warmstart was formed
  * before M was factorised in place, and M qacc_smooth = qfrc_smooth (qacc_smooth solves exactly that system; MJX
  * multiplies it out again, which differs by solve round-off only). */
@@ -1636,7 +1679,9 @@ RR_DEV void solve_constraints(Ctx<NS> &c) {
 #else
       mul_m<NS>(c, mv, search); /* leaves search staged in vbuf */
 #endif
+      prof<NS>(c, RR_PROF_LS_PRE);
       mul_j<NS>(c, c.row_jv);
+      prof<NS>(c, RR_PROF_LS_MULJ);
       float g0 = gauss, g1 = 0.f, g2 = 0.f;
       RR_FOR_S { g1 += search[s] * (Ma[s] - c.qfrc_smooth[s]); g2 += search[s] * mv[s]; }
 #pragma unroll
@@ -1656,6 +1701,7 @@ RR_DEV void solve_constraints(Ctx<NS> &c) {
         lo = r1[0];
       }
       if (lo.d0 < p0.d0) { hi = p0; } else { hi = lo; lo = p0; }
+      prof<NS>(c, RR_PROF_LS_EVAL2);
       bool swap = true;
       int ls_iter = 0;
       for (;;) {
@@ -1666,7 +1712,7 @@ RR_DEV void solve_constraints(Ctx<NS> &c) {
         if (done) break;
         float a3[3] = {lo.alpha - lo.d0 * RR_RCP(lo.d1), hi.alpha - hi.d0 * RR_RCP(hi.d1), 0.5f * (lo.alpha + hi.alpha)};
         LSPoint r3[3];
-        ls_eval<NS, 3>(c, nra, a3, g0, g1, g2, r3);
+        ls_eval3<NS>(c, nra, a3, g0, g1, g2, r3);
         LSPoint lo_next = r3[0], hi_next = r3[1], mid = r3[2];
         bool swap_lo_next = (lo.d0 > 0.f) || (lo.d0 < lo_next.d0);
         if (swap_lo_next) lo = lo_next;
@@ -1679,6 +1725,7 @@ RR_DEV void solve_constraints(Ctx<NS> &c) {
         swap = swap_lo_next | swap_lo_mid | swap_hi_next | swap_hi_mid;
         ls_iter++;
       }
+      prof<NS>(c, RR_PROF_LS_LOOP);
       bool improved = (lo.cost < p0.cost) || (hi.cost < p0.cost);
       float alpha = lo.cost < hi.cost ? lo.alpha : hi.alpha;
       if (improved) {
@@ -1695,6 +1742,7 @@ RR_DEV void solve_constraints(Ctx<NS> &c) {
     prev_cost = cost;
     prof<NS>(c, RR_PROF_SOLVE_UPD);
     cost = constraint_cost<NS>(c, c.qacc, Ma, gauss, true);
+    prof<NS>(c, RR_PROF_COST);
     mul_jt<NS>(c, c.row_jv, c.qfrc_constraint);
     prof<NS>(c, RR_PROF_CRB); /* profiling bucket "crb" = constraint_cost + J' f inside the solver */
     RR_FOR_S { grad[s] = Ma[s] - c.qfrc_smooth[s] - c.qfrc_constraint[s]; Mgrad[s] = grad[s]; }
@@ -1772,6 +1820,8 @@ RR_DEV void substep(Ctx<NS> &c, bool integrate, float &time, int sub) {
   const RRModelDev &m = c.m;
   const float dt = m.timestep;
   RR_CTA_SYNC_IF(RR_SYNC_LEVEL >= 1 && sub % RR_SYNC_PERIOD == 0);
+  __syncwarp();
+  prof<NS>(c, RR_PROF_WAIT);
   kinematics<NS>(c);
   prof<NS>(c, RR_PROF_FK);
   com_pos<NS>(c);
@@ -1794,12 +1844,16 @@ RR_DEV void substep(Ctx<NS> &c, bool integrate, float &time, int sub) {
   if (c.last_substep) forward_outputs<NS>(c);
   dbg_copy<NS>(c, RR_DBG_M, c.M, m.nM);
   mul_m<NS>(c, c.ma_warm, c.warm); /* the only product with M the solver needs (see ctx_init) */
+  prof<NS>(c, RR_PROF_MULM);
   RR_CTA_SYNC_IF(RR_SYNC_LEVEL >= 2 && RR_SYNC_FACTOR);
+  __syncwarp();
+  prof<NS>(c, RR_PROF_WAIT2);
 #if RR_FACTOR_RL
   factor2_rl<NS>(c, dt);
 #else
   factor2<NS>(c, dt);
 #endif
+  prof<NS>(c, RR_PROF_FACTOR2);
   for (int pass = 0; pass < 2; pass++) {
     float x[NS];
     RR_FOR_S x[s] = pass ? c.qfrc_smooth[s] + c.qfrc_constraint[s] : c.qfrc_smooth[s];

@@ -235,13 +235,13 @@ inline void rr_host_model_build(RRHostModel &hm, const int32_t *dir, const int32
     for (int i = 0; i < nv; i++) {
       int lw = 0;
       while ((1 << lw) < t_dof_depth[i] + 1 && lw < 5) lw++;
-      /* bit 8: rows i and i - 1 can be eliminated in one step (i - 1 is i's parent and has no other child; the row fits
-       * one register per lane).  The sweep runs from nv - 1 down and takes pairs greedily from the leaf end of a chain. */
-      /* the staging area of factor2 is the (dead) cinert array: 10 nbody floats for 4 (8 when paired) floats per descendant */
-      if (4 * t_dof_ndesc[i] > 10 * nb) throw std::runtime_error("NotImplemented: more dofs below one dof than 2.5 x nbody");
-      bool pair = i >= 1 && dofparent[i] == i - 1 && nchild[i - 1] == 1 && t_dof_depth[i] >= 1 && t_dof_depth[i] < 32 &&
-                  8 * t_dof_ndesc[i] <= 10 * nb;
-      t_dof_log2w[i] = lw | (pair ? 256 : 0);
+      /* bits 8-9: T - 1, the number of rows i-1 .. i-T+1 eliminated in the same step as row i (each the parent of the one
+       * below with no other child; the row fits one register per lane).  factor2 sweeps from nv - 1 down and takes groups
+       * greedily from the leaf end of a chain, so only the entry of a group's deepest row is read. */
+      int T = 1;
+      if (t_dof_depth[i] < 32)
+        while (T < 4 && i - T >= 0 && dofparent[i - T + 1] == i - T && nchild[i - T] == 1 && t_dof_depth[i - T] >= 0) T++;
+      t_dof_log2w[i] = lw | ((T - 1) << 8);
     }
   }
   {
@@ -376,7 +376,7 @@ inline void rr_host_model_build(RRHostModel &hm, const int32_t *dir, const int32
   int o = 0;
   auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };
   s.qpos = take(nq); s.qvel = take(nv); s.act = take(d.na); s.ctrl = take(nu); s.actdot = take(d.na);
-  s.com = take(3 * d.nroot); s.vbuf = take(nv);  s.xq1 = take(4); s.prof_acc = take(16);
+  s.com = take(3 * d.nroot); s.vbuf = take(nv);  s.xq1 = take(4); s.prof_acc = take(32);
   s.M = take(nM); s.LD = take(std::max(nM, 8 * nb)); /* LD doubles as the second buffer of the tree scans (8 floats per body) */
   s.xpos = take(3 * nb); s.xquat = take(4 * nb); s.cdof = take(6 * nv);
   const int c0 = o;
@@ -387,6 +387,8 @@ inline void rr_host_model_build(RRHostModel &hm, const int32_t *dir, const int32
   int c1_end = o;
   o = c1b; s.crb = take(10 * nb); s.fcrb = s.crb;
   c1_end = std::max(c1_end, o);
+  /* factor2 stages 9 floats per descendant of a row in the C1 span (dead by then) */
+  if (9 * ((nv + 3) & ~3) > c1_end - c0) throw std::runtime_error("NotImplemented: factorisation staging does not fit (nv >> nbody)");
   /* C2: contact arrays, then as many constraint rows (5 arrays) as fit in the recycled span */
   o = c0;
   s.capA = std::min(nc, 32); /* active contacts whose six-vectors stay in shared memory (more go to the global scratch) */
