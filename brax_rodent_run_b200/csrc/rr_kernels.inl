@@ -48,6 +48,30 @@
 #ifndef RR_CTA_SYNC
 #define RR_CTA_SYNC() __syncthreads()
 #endif
+#ifndef RR_DUP_SOLVE
+#define RR_DUP_SOLVE 0
+#endif
+#ifndef RR_DUP_MULJ
+#define RR_DUP_MULJ 0
+#endif
+#ifndef RR_DUP_MULJT
+#define RR_DUP_MULJT 0
+#endif
+#ifndef RR_DUP_LS
+#define RR_DUP_LS 0
+#endif
+#ifndef RR_DUP_KIN
+#define RR_DUP_KIN 0
+#endif
+#ifndef RR_DUP_RNE
+#define RR_DUP_RNE 0
+#endif
+#ifndef RR_DUP_CRB
+#define RR_DUP_CRB 0
+#endif
+#ifndef RR_DUP_FACTOR
+#define RR_DUP_FACTOR 0
+#endif
 #ifndef RR_MV_RECURRENCE
 #define RR_MV_RECURRENCE 1
 #endif
@@ -1680,7 +1704,8 @@ RR_DEV void solve_constraints(Ctx<NS> &c) {
       mul_m<NS>(c, mv, search); /* leaves search staged in vbuf */
 #endif
       prof<NS>(c, RR_PROF_LS_PRE);
-      mul_j<NS>(c, c.row_jv);
+#pragma unroll 1
+      for (int rep = 0; rep <= RR_DUP_MULJ; rep++) mul_j<NS>(c, c.row_jv);
       prof<NS>(c, RR_PROF_LS_MULJ);
       float g0 = gauss, g1 = 0.f, g2 = 0.f;
       RR_FOR_S { g1 += search[s] * (Ma[s] - c.qfrc_smooth[s]); g2 += search[s] * mv[s]; }
@@ -1712,7 +1737,8 @@ RR_DEV void solve_constraints(Ctx<NS> &c) {
         if (done) break;
         float a3[3] = {lo.alpha - lo.d0 * RR_RCP(lo.d1), hi.alpha - hi.d0 * RR_RCP(hi.d1), 0.5f * (lo.alpha + hi.alpha)};
         LSPoint r3[3];
-        ls_eval3<NS>(c, nra, a3, g0, g1, g2, r3);
+#pragma unroll 1
+        for (int rep = 0; rep <= RR_DUP_LS; rep++) ls_eval3<NS>(c, nra, a3, g0, g1, g2, r3);
         LSPoint lo_next = r3[0], hi_next = r3[1], mid = r3[2];
         bool swap_lo_next = (lo.d0 > 0.f) || (lo.d0 < lo_next.d0);
         if (swap_lo_next) lo = lo_next;
@@ -1743,10 +1769,15 @@ RR_DEV void solve_constraints(Ctx<NS> &c) {
     prof<NS>(c, RR_PROF_SOLVE_UPD);
     cost = constraint_cost<NS>(c, c.qacc, Ma, gauss, true);
     prof<NS>(c, RR_PROF_COST);
-    mul_jt<NS>(c, c.row_jv, c.qfrc_constraint);
+#pragma unroll 1
+    for (int rep = 0; rep <= RR_DUP_MULJT; rep++) mul_jt<NS>(c, c.row_jv, c.qfrc_constraint);
     prof<NS>(c, RR_PROF_CRB); /* profiling bucket "crb" = constraint_cost + J' f inside the solver */
-    RR_FOR_S { grad[s] = Ma[s] - c.qfrc_smooth[s] - c.qfrc_constraint[s]; Mgrad[s] = grad[s]; }
-    solve_ld<NS>(c, Mgrad, c.LD, c.dinv);
+    RR_FOR_S { grad[s] = Ma[s] - c.qfrc_smooth[s] - c.qfrc_constraint[s]; }
+#pragma unroll 1
+    for (int rep = 0; rep <= RR_DUP_SOLVE; rep++) {
+      RR_FOR_S Mgrad[s] = grad[s];
+      solve_ld<NS>(c, Mgrad, c.LD, c.dinv);
+    }
     prof<NS>(c, RR_PROF_VEL); /* profiling bucket "com_vel" = the M^-1 grad solve inside the solver */
     if (first) {
       RR_FOR_S search[s] = -Mgrad[s];
@@ -1822,7 +1853,8 @@ RR_DEV void substep(Ctx<NS> &c, bool integrate, float &time, int sub) {
   RR_CTA_SYNC_IF(RR_SYNC_LEVEL >= 1 && sub % RR_SYNC_PERIOD == 0);
   __syncwarp();
   prof<NS>(c, RR_PROF_WAIT);
-  kinematics<NS>(c);
+#pragma unroll 1
+  for (int rep = 0; rep <= RR_DUP_KIN; rep++) kinematics<NS>(c);
   prof<NS>(c, RR_PROF_FK);
   com_pos<NS>(c);
   prof<NS>(c, RR_PROF_COM);
@@ -1831,11 +1863,13 @@ RR_DEV void substep(Ctx<NS> &c, bool integrate, float &time, int sub) {
   dbg_copy<NS>(c, RR_DBG_COM, c.com, 3 * m.nroot);
   dbg_copy<NS>(c, RR_DBG_CINERT, c.cinert, 10 * m.nbody);
   dbg_copy<NS>(c, RR_DBG_CDOF, c.cdof, 6 * m.nv);
-  crb_and_mass_matrix<NS>(c);
+#pragma unroll 1
+  for (int rep = 0; rep <= RR_DUP_CRB; rep++) crb_and_mass_matrix<NS>(c);
   prof<NS>(c, RR_PROF_QM);
   {
     float qfrc_bias[NS];
-    com_vel_and_rne<NS>(c, qfrc_bias);
+#pragma unroll 1
+    for (int rep = 0; rep <= RR_DUP_RNE; rep++) com_vel_and_rne<NS>(c, qfrc_bias);
     prof<NS>(c, RR_PROF_RNE);
     dbg_copy<NS>(c, RR_DBG_CVEL, c.cvel, 6 * m.nbody);
     smooth_forces<NS>(c, qfrc_bias);
