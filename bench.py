@@ -31,11 +31,15 @@ sys.path.insert(0, ROOT)
 ENVS_PER_GPU = 4096
 N_FRAMES = 10
 ALGO_BYTES_PER_ENV_STEP = 7204  # state in/out + action + 1263-float obs + scalars
-FP32_PEAK_TFLOPS_NOMINAL = 148 * 128 * 2 * 1.965e9 / 1e12  # 74.4, no measured FP32 peak in MEASURED_PEAKS.json
-# dram__bytes_read.sum + dram__bytes_write.sum of one rr_step_kernel launch (profiles/r01_v17_ncu_raw.csv, `ncu --set full`):
-# 5.58 MB + 0.34 MB.  Below the algorithmic 29.5 MB because the 25 MB of state / observation written by a launch is still
+FP32_PEAK_TFLOPS_NOMINAL = 148 * 128 * 2 * 1.965e9 / 1e12  # 74.4; the bench line reports the MEASURED peak (rr_measure_fp32_peak)
+# dram__bytes_read.sum + dram__bytes_write.sum of one rr_step_kernel launch (profiles/r02_kpar_ncu_raw.csv, `ncu --set full`):
+# 5.25 MB + 0.26 MB.  Below the algorithmic 29.5 MB because the 25 MB of state / observation written by a launch is still
 # resident in the 126 MB L2 when the kernel ends.
-NCU_DRAM_TRAFFIC_BYTES_PER_LAUNCH = 5_579_008 + 337_152
+NCU_DRAM_TRAFFIC_BYTES_PER_LAUNCH = 5_245_184 + 259_584
+# FP32 operations per env-step counted by ncu on the same launch (smsp__sass_thread_inst_executed_op_{fadd,fmul,ffma x 2}_pred_on,
+# profiles/r02_kpar_ncu_raw.csv): 1.0912e10 per 4096-env launch.  What the kernel EXECUTES (tree-sparse, active rows only); the
+# roofline numerator is the oracle's operation count of the reference's dense formulation with non-zero operands (below).
+NCU_FLOPS_PER_ENV_STEP = 1.0912e10 / 4096
 
 
 def synthetic_track(n=250):
@@ -77,6 +81,34 @@ def _oracle_steps(n_steps):
         if done or _W["steps"] >= 1000:  # terminate_when_unhealthy / episode_length, as the B200 arm's fused wrappers
             _oracle_reset()
     return time.perf_counter() - t0
+
+
+def oracle_flops_per_env_step(iterations, ls_iterations, model="rodent_0", envs=2, steps=12, settle=8):
+    """Operation count of one env step from the instrumented oracle (oracle/rr_oracle_count.cpp): (total, useful) FP operations of
+    the reference's dense formulation, averaged over a bounded random-action sample (`envs` x `steps` after `settle` steps).
+    'useful' drops operations on structural zeros (a product with a zero operand, a sum of two zeros): the sparsity-exact count
+    SURVEY 8(d) asks for."""
+    from brax_rodent_run_b200 import mjcf, model_blob
+    from oracle import oracle
+    oracle.build()
+    m = mjcf.FlatModel.load(os.path.join(ROOT, "brax_rodent_run_b200", "assets", f"{model}.npz"))
+    blob = model_blob.pack(m)
+    tot = use = n = 0
+    for e in range(envs):
+        rng = np.random.default_rng(100 + e)
+        env = oracle.OracleRodentEnv(blob, (m.nq, m.nv, m.nu, m.nbody), synthetic_track(), iterations=iterations,
+                                     ls_iterations=ls_iterations, precision="cnt")
+        q = m.qpos0.copy()
+        sf = int(rng.integers(0, 100))
+        q[:3] = synthetic_track()[sf]
+        env.reset(sf, q + rng.uniform(-.01, .01, m.nq), rng.uniform(-.01, .01, m.nv))
+        for t in range(settle + steps):
+            if t == settle:
+                env.o.ops(reset=True)
+            env.step(rng.uniform(-1, 1, m.nu))
+        a, b = env.o.ops(reset=True)
+        tot, use, n = tot + a, use + b, n + steps
+    return tot / n, use / n
 
 
 class OraclePool:
@@ -147,7 +179,7 @@ class ClockSampler:
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
@@ -199,7 +231,7 @@ def run_b200(args):
     B, K, W = args.envs, args.steps, args.warmup
     env = Rodent(synthetic_track(), num_envs=B, device=dev, model=args.model, solver="cg", iterations=args.iterations,
                  ls_iterations=args.ls_iterations, terminate_when_unhealthy=True, kinematics_outputs=False,
-                 balance=args.balance)
+                 balance=args.balance, _lib_path=args.lib)
     env.wrap_for_training(episode_length=1000)
     L = env._L
     gen = torch.Generator(device=dev)
@@ -231,7 +263,6 @@ def run_b200(args):
     barrier()
     wall = time.perf_counter() - t_wall0
     launches = L.rr_launch_count() - launches0
-    clocks = sampler.stop() if sampler else None
     ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = float(sum(ms))
     t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
@@ -275,6 +306,12 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * B * Ke / float(t.item())
+    clocks = sampler.stop() if sampler else None  # sampled every 20 ms over the device-timed loop and the end-to-end loop
+    fp32_peak = ctypes.c_double(0.0)
+    _lib.check(L, L.rr_measure_fp32_peak(ctypes.byref(fp32_peak), stream))
+    extra = {}
+    if not args.no_extra:
+        extra = measure_extra(args, dev, world, rank)
     h2d = B * env.action_size * 4
     d2h = B * (env.observation_size + 2) * 4
 
@@ -290,25 +327,39 @@ def run_b200(args):
         algo_bytes = 4 * (2 * (d_.nq + 2 * d_.nv + d_.na) + env.action_size + d_.obs_dim + 8)
         assert args.model != "rodent_0" or algo_bytes == ALGO_BYTES_PER_ENV_STEP
         achieved_gbs = algo_bytes * B / (kernel_ms * 1e-3) / 1e9
-        flops_per_env_step = 10 * (182e3 + args.iterations * (22962 + 1421 * (2 + 3 * args.ls_iterations)))
-        achieved_tflops = flops_per_env_step * B / (kernel_ms * 1e-3) / 1e12
+        kernel_name = "rr_step_kernel<3>" if d_.nv <= 96 else "rr_step_kernel<5>"
+        # FP32 roofline (the binding roof): operations per env-step from the instrumented oracle on a bounded
+        # sample of the same workload, divided by the FMA throughput measured on this device just now
+        flops_total, flops_useful = oracle_flops_per_env_step(args.iterations, args.ls_iterations, args.model)
+        achieved_tflops = flops_useful * B / (kernel_ms * 1e-3) / 1e12
+        peak_tf = float(fp32_peak.value)
         out = {
             "metric": "rodent env-steps/s", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(args),
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke},
             "gpu_launches": int(launches), "clocks": clocks,
-            "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": peak_gbs, "unit": "GB/s", "frac": achieved_gbs / peak_gbs,
+            "roofline": {"bound": "fp32", "achieved": achieved_tflops, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": achieved_tflops / peak_tf if peak_tf > 0 else None,
                          "traffic": NCU_DRAM_TRAFFIC_BYTES_PER_LAUNCH if (args.model, B) == ("rodent_0", ENVS_PER_GPU) else None,
-                         "algorithmic_bytes": algo_bytes * B, "peak_source": peak_src, "kernel": "rr_step_kernel<3>" if d_.nv <= 96 else "rr_step_kernel<5>",
-                         "note": "the kernel is FP32-issue/latency bound, not HBM bound (SURVEY 8d); see roofline_fp32"},
-            "roofline_fp32": {"achieved": achieved_tflops, "peak": FP32_PEAK_TFLOPS_NOMINAL, "unit": "TFLOP/s",
-                              "frac": achieved_tflops / FP32_PEAK_TFLOPS_NOMINAL, "peak_source": "nominal 148 SM x 128 lanes x 2 x 1.965 GHz",
-                              "flops_per_env_step": flops_per_env_step, "flops_source": "SURVEY 8(d) dense-row operation-count estimate (upper bound: the kernel skips inactive rows)"},
+                         "kernel": kernel_name,
+                         "peak_source": "measured in this run: rr_measure_fp32_peak (8 FMA chains per thread on every SM); nominal "
+                                        f"{FP32_PEAK_TFLOPS_NOMINAL:.1f}",
+                         "flops_per_env_step": flops_useful, "flops_per_env_step_dense": flops_total,
+                         "flops_per_env_step_ncu": NCU_FLOPS_PER_ENV_STEP if args.model == "rodent_0" else None,
+                         "flops_source": "oracle/rr_oracle_count.cpp: FP operations with non-zero operands of the reference's dense "
+                                         "formulation, 2 envs x 12 random-action env steps; _dense counts every operation; _ncu is "
+                                         "what the kernel executes (tree-sparse, active rows only; profiles/r02_kpar_ncu_raw.csv)",
+                         "note": "irregular 73-wide tree arithmetic: bound by FP32 issue / dependent-chain latency, not by HBM "
+                                 "(7.2 KB per env-step); see roofline_hbm"},
+            "roofline_hbm": {"bound": "hbm", "achieved": achieved_gbs, "peak": peak_gbs, "unit": "GB/s", "frac": achieved_gbs / peak_gbs,
+                             "algorithmic_bytes": algo_bytes * B, "peak_source": peak_src},
             "wall_s": wall, "done_frac_last_step": done_frac,
         }
-        if args.model != "rodent_0":
-            out.pop("roofline_fp32")  # the operation-count estimate is rodent_0's
+        if args.lib:
+            out["lib_override"] = args.lib
+        if extra:
+            out["extra"] = extra
         if world == 1 and not args.no_cpu_baseline:
             pool = OraclePool(args.iterations, args.ls_iterations, model=args.model)
             pool.rate(5)
@@ -321,6 +372,68 @@ def run_b200(args):
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------ extras on the bench line
+def measure_extra(args, dev, world, rank):
+    """The other half of BASELINE.json's metric and configs[4], measured after the timed region of the contract line and
+    appended to the same JSON line: PPO train SPS (2048 envs / GPU, README configuration, NCCL gradient all-reduce when
+    world > 1) and rodent_pair env-steps/s (4096 envs / GPU).  Bounded: 1 + 2 training steps, 3 + 10 env steps."""
+    import torch
+    import torch.distributed as dist
+    from brax_rodent_run_b200 import ppo
+    from brax_rodent_run_b200.env import Rodent
+    out = {}
+    try:
+        env = Rodent(synthetic_track(), num_envs=2048, device=dev, model="rodent_0", iterations=args.iterations,
+                     ls_iterations=args.ls_iterations, terminate_when_unhealthy=False, kinematics_outputs=False)
+        cfg = ppo.PPOConfig(num_envs=2048)
+        agent = ppo.PPO(env.wrap_for_training(cfg.episode_length), cfg)
+        state = env.reset(rank)
+        state, _ = agent.training_step(state)
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        e0, t0 = agent.env_steps, time.perf_counter()
+        for _ in range(2):
+            state, _ = agent.training_step(state)
+        torch.cuda.synchronize(dev)
+        dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        out["ppo_train_sps"] = {"value": (agent.env_steps - e0) / float(dt.item()), "unit": "env-steps/s", "envs_per_gpu": 2048,
+                                "n_gpus": world, "training_steps": 2,
+                                "config": "readme.md:17-31: unroll 10, batch 512 x 64 minibatches, 8 epochs, CG 8/8, normalised obs"}
+        del agent, env, state
+    except Exception as ex:  # the contract line must survive a failure of an extra
+        out["ppo_train_sps"] = {"error": repr(ex)[:200]}
+    try:
+        B = ENVS_PER_GPU
+        env = Rodent(synthetic_track(), num_envs=B, device=dev, model="rodent_pair", iterations=args.iterations,
+                     ls_iterations=args.ls_iterations, kinematics_outputs=False).wrap_for_training(1000)
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(99 + rank)
+        state = env.reset(gen)
+        acts = torch.rand((13, B, env.action_size), generator=gen, device=dev) * 2 - 1
+        for i in range(3):
+            state = env.step(state, acts[i])
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(10):
+            state = env.step(state, acts[3 + i])
+        e1.record()
+        torch.cuda.synchronize(dev)
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out["rodent_pair"] = {"value": world * B * 10 / (float(t.item()) * 1e-3), "unit": "env-steps/s", "envs_per_gpu": B,
+                              "n_gpus": world, "ms_per_step": float(t.item()) / 10, "steps": 10}
+    except Exception as ex:
+        out["rodent_pair"] = {"error": repr(ex)[:200]}
+    return out
 
 
 # ------------------------------------------------------------------------------------------------ PPO train SPS
@@ -388,6 +501,8 @@ def main():
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="environments per GPU")
     ap.add_argument("--workload", default="step", choices=["step", "ppo"],
                     help="step: env-steps/s of Rodent.step (the contract line, default); ppo: PPO train SPS")
+    ap.add_argument("--no-extra", action="store_true", help="skip the PPO-train-SPS / rodent_pair extras appended to the bench line")
+    ap.add_argument("--lib", default=None, help="developer knob: A/B a kernel build (variants/librr_<name>.so); recorded in the line")
     ap.add_argument("--balance", action="store_true",
                     help="cost-sorted env -> CTA assignment (off: measured slower than the even contiguous split, see DESIGN.md)")
     args = ap.parse_args()

@@ -57,7 +57,7 @@ _libs = {}
 
 def load(path: Optional[str] = None):
     """Load (once) and type the shared library.  `path=None` is the CUDA product library."""
-    path = path or os.environ.get("RR_B200_LIB") or LIB_PATH  # RR_B200_LIB: developer hook to A/B kernel builds
+    path = path or LIB_PATH
     if path in _libs:
         return _libs[path]
     if not os.path.exists(path):
@@ -90,6 +90,8 @@ def load(path: Optional[str] = None):
     L.rr_prof_count.restype = ctypes.c_int
     L.rr_prof_name.argtypes = [ctypes.c_int32]
     L.rr_prof_name.restype = ctypes.c_char_p
+    L.rr_measure_fp32_peak.argtypes = [ctypes.POINTER(ctypes.c_double), vp]
+    L.rr_measure_fp32_peak.restype = ctypes.c_int
     L.rr_launch_count.restype = ctypes.c_longlong
     for name in ("rr_model_create", "rr_model_set_solver", "rr_model_dims", "rr_env_create", "rr_env_set_task",
                  "rr_env_set_wrappers", "rr_env_geometry", "rr_env_init", "rr_env_step", "rr_env_step_host", "rr_gae", "rr_debug_field",

@@ -137,6 +137,21 @@ __global__ void __launch_bounds__(RR_PPO_THREADS) rr_ppo_loss_b_kernel(const __g
   if (threadIdx.x < 3) a.loss_partial[3 * blockIdx.x + threadIdx.x] = sh[threadIdx.x][0];
 }
 
+/* FP32 FMA peak: 8 independent chains per thread (latency 4 cycles x 2 issue ports needs >= 8 in flight per thread pair) */
+__global__ void __launch_bounds__(256) rr_fma_peak_kernel(float *out, int iters) {
+  float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
+  const float m = 0.9999f, c = 1e-4f;
+#pragma unroll 1
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int u = 0; u < 16; u++) {
+      a0 = fmaf(a0, m, c); a1 = fmaf(a1, m, c); a2 = fmaf(a2, m, c); a3 = fmaf(a3, m, c);
+      a4 = fmaf(a4, m, c); a5 = fmaf(a5, m, c); a6 = fmaf(a6, m, c); a7 = fmaf(a7, m, c);
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
 static thread_local char g_cuda_err[256];
 static const char *rrb_error() { return g_cuda_err; }
 static int rrb_check(cudaError_t e, const char *what) {
@@ -165,6 +180,35 @@ static void *rrb_host_devptr(void *host) {
   return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
 }
 static int rrb_sync(void *stream) { return rrb_check(cudaStreamSynchronize((cudaStream_t)stream), "cudaStreamSynchronize"); }
+
+static int rrb_fp32_peak(double *tflops, void *stream) {
+  int dev = 0, n_sm = 0;
+  if (rrb_check(cudaGetDevice(&dev), "cudaGetDevice") ||
+      rrb_check(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev), "cudaDeviceGetAttribute"))
+    return 1;
+  const int ctas = n_sm * 8, threads = 256, iters = 4096;
+  float *out = nullptr;
+  if (rrb_check(cudaMalloc(&out, (size_t)ctas * threads * sizeof(float)), "cudaMalloc")) return 1;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaStream_t st = (cudaStream_t)stream;
+  rr_fma_peak_kernel<<<ctas, threads, 0, st>>>(out, 64);
+  double best = 0.0;
+  for (int rep = 0; rep < 3; rep++) {
+    cudaEventRecord(e0, st);
+    rr_fma_peak_kernel<<<ctas, threads, 0, st>>>(out, iters);
+    cudaEventRecord(e1, st);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double flops = 2.0 * 8 * 16 * (double)iters * ctas * threads;
+    if (ms > 0.f) best = best > flops / (ms * 1e-3) / 1e12 ? best : flops / (ms * 1e-3) / 1e12;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(out);
+  *tflops = best;
+  return rrb_check(cudaGetLastError(), "rr_fma_peak_kernel");
+}
 
 static int rrb_max_wpb(const RRModelDev &m) { return m.nv <= 96 ? RRMaxWpb<3>::value : RRMaxWpb<5>::value; }
 

@@ -345,3 +345,10 @@ extern "C" int rr_ppo_loss(const rr_ppo_loss_args *u, void *stream) {
   g_rr_launches += 2;
   return RR_OK;
 }
+
+extern "C" int rr_measure_fp32_peak(double *tflops, void *stream) {
+  if (!tflops) return rr_fail(RR_EINVAL, "rr_measure_fp32_peak: null argument");
+  if (rrb_fp32_peak(tflops, stream)) return rr_fail(RR_ECUDA, rrb_error());
+  g_rr_launches += 4;
+  return RR_OK;
+}

@@ -147,6 +147,10 @@ int rr_env_set_debug(rr_env *e, float *dbg /* DEVICE [B, debug_stride] or null *
 int rr_env_set_profile(rr_env *e, long long *prof);
 int rr_prof_count(void);
 const char *rr_prof_name(int32_t i);
+/* Measured FP32 FMA throughput of the current device (TFLOP/s, 2 flops per FMA): 8 independent FMA chains per thread on
+ * every SM for ~10 ms, timed with CUDA events on `stream`.  The denominator of bench.py's FP32 roofline;
+ * no counterpart in the reference. */
+int rr_measure_fp32_peak(double *tflops, void *stream);
 /* number of kernels launched by this library since load (bench.py's gpu_launches) */
 long long rr_launch_count(void);
 

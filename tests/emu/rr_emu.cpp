@@ -138,6 +138,7 @@ static int rrb_d2h(void *dst, const void *src, size_t bytes, void *) { memcpy(ds
 static void *rrb_host_devptr(void *) { return nullptr; }
 static int rrb_sync(void *) { return 0; }
 static int rrb_num_slots() { return 1; }
+static int rrb_fp32_peak(double *, void *) { return 1; } /* no device: the call fails with RR_ECUDA */
 static int rrb_geometry(const RRModelDev &, int B, int *ctas, int *wpb) { *ctas = B; *wpb = 1; return 0; }
 
 struct EmuJob { const RRModelDev *m; const RRStepArgs *a; int env; float *sm; const int32_t *ti; const float *tf; };

@@ -3,7 +3,7 @@
 out=gpurun_out/ab.txt; : > $out
 for spec in "$@"; do
   v=${spec%%:*}; flags=""; [[ "$spec" == *:* ]] && flags=${spec#*:}
-  RR_B200_LIB=$PWD/variants/librr_$v.so python bench.py --steps 30 --warmup 5 --no-cpu-baseline $flags 2>&1 | python -c "
+  python bench.py --steps 30 --warmup 5 --no-cpu-baseline --no-extra --lib $PWD/variants/librr_$v.so $flags 2>&1 | python -c "
 import sys,json
 for l in sys.stdin:
     try: d=json.loads(l); print('$spec', round(d['value']), round(d['ms_per_step'],3))

@@ -1,5 +1,5 @@
 #!/bin/bash
-# tools/build_variant.sh NAME [-DKNOB=VALUE ...]  ->  variants/librr_NAME.so (A/B kernel builds; select with RR_B200_LIB)
+# tools/build_variant.sh NAME [-DKNOB=VALUE ...]  ->  variants/librr_NAME.so (A/B kernel builds; select with bench.py --lib)
 set -e
 cd "$(dirname "$0")/.."
 name=$1; shift
