@@ -33,7 +33,7 @@ _BUF_FIELDS = (
     "obs", "reward", "done", "metrics", "steps", "truncation",
     "first_qpos", "first_qvel", "first_act", "first_qacc_warmstart", "first_time", "first_obs",
     "xpos", "xquat", "subtree_com", "qfrc_actuator", "cinert", "cvel", "contact_dist", "qacc", "solver_niter",
-    "work", "env_order",
+    "work", "env_order", "contact_pos", "contact_frame",
 )
 
 

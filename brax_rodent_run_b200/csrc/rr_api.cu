@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <math_constants.h>
+#include <atomic>
 
 /* production kernels: debug-dump / clock64 hooks compiled out */
 #define RR_NS rr
@@ -241,15 +242,15 @@ static int rrb_launch_ns(const RRModelDev &m, const RRStepArgs &a, void *stream)
   int grid = 1, wpb = 1;
   if (rrb_geometry(m, a.B, &grid, &wpb)) return 1;
   const size_t smem = ((size_t)m.ni + m.nf) * 4 + (size_t)m.sm.total * sizeof(float) * wpb;
-  static bool configured[64] = {false};
+  static std::atomic<bool> configured[64]; /* per device; the attribute call is idempotent, so a race only repeats it */
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64) dev = 0;
-  if (!configured[dev]) {
+  if (!configured[dev].load(std::memory_order_acquire)) {
     if (rrb_check(cudaFuncSetAttribute(rr_step_kernel<NS, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, RR_SMEM_MAX),
                   "cudaFuncSetAttribute(smem)"))
       return 1;
-    configured[dev] = true;
+    configured[dev].store(true, std::memory_order_release);
   }
   rr_step_kernel<NS, DBG><<<grid, 32 * wpb, smem, (cudaStream_t)stream>>>(m, a);
   return rrb_check(cudaGetLastError(), "rr_step_kernel launch");

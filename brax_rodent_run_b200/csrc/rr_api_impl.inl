@@ -28,14 +28,14 @@ static std::atomic<long long> g_rr_launches{0};
 
 struct rr_model {
   RRHostModel host;
-  RRModelDev dev;  /* pointers bound to device copies */
-  int32_t *d_ibuf;
-  float *d_fbuf;
+  RRModelDev dev;  /* scalars, layout and table offsets; the table POINTERS are per environment (one copy per device) */
 };
 
 struct rr_env {
   const rr_model *model;
   int B, device;
+  int32_t *d_ibuf; /* this environment's device copy of the model tables (an rr_model may serve several devices) */
+  float *d_fbuf;
   RRTask task;
   float *d_track;
   int episode_length;
@@ -61,8 +61,6 @@ extern "C" int rr_model_create(const int32_t *dir, int32_t ndir, const int32_t *
   for (int k = 0; k < RR_NFIELDS; k++)
     if (dir[2 * k] < 0 || dir[2 * k + 1] < 0) return rr_fail(RR_EINVAL, "rr_model_create: negative offset in blob directory");
   rr_model *m = new rr_model();
-  m->d_ibuf = nullptr;
-  m->d_fbuf = nullptr;
   try {
     rr_host_model_build(m->host, dir, idata, ni, fdata, nf);
   } catch (const std::exception &ex) {
@@ -71,14 +69,13 @@ extern "C" int rr_model_create(const int32_t *dir, int32_t ndir, const int32_t *
     return rr_fail(msg.rfind("NotImplemented", 0) == 0 ? RR_ENOTIMPL : RR_EINVAL, msg);
   }
   m->dev = m->host.dev;
+  rr_host_model_bind(m->host, m->dev, nullptr, nullptr); /* table offsets; pointers are bound per environment */
   *out = m;
   return RR_OK;
 }
 
 extern "C" void rr_model_destroy(rr_model *m) {
   if (!m) return;
-  if (m->d_ibuf) rrb_free(m->d_ibuf);
-  if (m->d_fbuf) rrb_free(m->d_fbuf);
   delete m;
 }
 
@@ -135,18 +132,20 @@ extern "C" const char *rr_prof_name(int32_t i) { return (i >= 0 && i < RR_NPROF)
 
 extern "C" int rr_env_create(const rr_model *cm, int32_t num_envs, int32_t device, rr_env **out) {
   if (!cm || !out || num_envs < 1) return rr_fail(RR_EINVAL, "rr_env_create: bad argument");
-  rr_model *m = const_cast<rr_model *>(cm);
+  const rr_model *m = cm;
   if (rrb_set_device(device)) return rr_fail(RR_ECUDA, rrb_error());
-  if (!m->d_ibuf) { /* first use: upload the tables */
-    if (rrb_malloc((void **)&m->d_ibuf, m->host.ibuf.size() * sizeof(int32_t)) ||
-        rrb_malloc((void **)&m->d_fbuf, m->host.fbuf.size() * sizeof(float)) ||
-        rrb_h2d(m->d_ibuf, m->host.ibuf.data(), m->host.ibuf.size() * sizeof(int32_t), nullptr) ||
-        rrb_h2d(m->d_fbuf, m->host.fbuf.data(), m->host.fbuf.size() * sizeof(float), nullptr) || rrb_sync(nullptr))
-      return rr_fail(RR_ECUDA, rrb_error());
-    rr_host_model_bind(m->host, m->dev, m->d_ibuf, m->d_fbuf);
-  }
   rr_env *e = new rr_env();
   std::memset(e, 0, sizeof(*e));
+  /* the model tables are uploaded per environment, on the environment's device */
+  if (rrb_malloc((void **)&e->d_ibuf, m->host.ibuf.size() * sizeof(int32_t)) ||
+      rrb_malloc((void **)&e->d_fbuf, m->host.fbuf.size() * sizeof(float)) ||
+      rrb_h2d(e->d_ibuf, m->host.ibuf.data(), m->host.ibuf.size() * sizeof(int32_t), nullptr) ||
+      rrb_h2d(e->d_fbuf, m->host.fbuf.data(), m->host.fbuf.size() * sizeof(float), nullptr) || rrb_sync(nullptr)) {
+    if (e->d_ibuf) rrb_free(e->d_ibuf);
+    if (e->d_fbuf) rrb_free(e->d_fbuf);
+    delete e;
+    return rr_fail(RR_ECUDA, rrb_error());
+  }
   e->model = m;
   e->B = num_envs;
   e->device = device;
@@ -156,12 +155,13 @@ extern "C" int rr_env_create(const rr_model *cm, int32_t num_envs, int32_t devic
   e->task.healthy_z_hi = 0.5f;
   e->task.terminate_when_unhealthy = 1;
   if (rrb_malloc((void **)&e->d_action_stage, (size_t)num_envs * (m->dev.nu > 0 ? m->dev.nu : 1) * sizeof(float))) {
+    rrb_free(e->d_ibuf); rrb_free(e->d_fbuf);
     delete e;
     return rr_fail(RR_ECUDA, rrb_error());
   }
   e->scratch_stride = 5 * ((m->dev.nefc + 3) & ~3) + 8 + 6 * ((m->dev.ncon + 3) & ~3); /* rows (5 nefc) + per-contact six-vectors */
   if (rrb_malloc((void **)&e->d_scratch, (size_t)rrb_num_slots() * e->scratch_stride * sizeof(float))) {
-    rrb_free(e->d_action_stage);
+    rrb_free(e->d_action_stage); rrb_free(e->d_ibuf); rrb_free(e->d_fbuf);
     delete e;
     return rr_fail(RR_ECUDA, rrb_error());
   }
@@ -174,6 +174,8 @@ extern "C" void rr_env_destroy(rr_env *e) {
   if (e->d_scratch) rrb_free(e->d_scratch);
   if (e->d_track) rrb_free(e->d_track);
   if (e->d_action_stage) rrb_free(e->d_action_stage);
+  if (e->d_ibuf) rrb_free(e->d_ibuf);
+  if (e->d_fbuf) rrb_free(e->d_fbuf);
   delete e;
 }
 
@@ -254,6 +256,7 @@ static int rr_fill_args(rr_env *e, const rr_buffers *b, const float *action, int
   a.xpos = b->xpos; a.xquat = b->xquat; a.subtree_com = b->subtree_com; a.qfrc_actuator = b->qfrc_actuator;
   a.cinert = b->cinert; a.cvel = b->cvel; a.contact_dist = b->contact_dist; a.qacc = b->qacc; a.niter = b->solver_niter;
   a.work = b->work; a.env_order = b->env_order;
+  a.contact_pos = b->contact_pos; a.contact_frame = b->contact_frame;
   a.dbg.buf = e->d_dbg;
   a.dbg.stride = rr_debug_stride_of(e->model->dev);
   a.prof = e->d_prof;
@@ -262,11 +265,19 @@ static int rr_fill_args(rr_env *e, const rr_buffers *b, const float *action, int
   return RR_OK;
 }
 
+/* the model's scalars / layout with THIS environment's device tables */
+static RRModelDev rr_env_dev(const rr_env *e) {
+  RRModelDev d = e->model->dev;
+  d.ibuf = e->d_ibuf;
+  d.fbuf = e->d_fbuf;
+  return d;
+}
+
 extern "C" int rr_env_init(rr_env *e, const rr_buffers *b, void *stream) {
   RRStepArgs a;
   int rc = rr_fill_args(e, b, nullptr, 0, RR_MODE_INIT, a);
   if (rc) return rc;
-  if (rrb_set_device(e->device) || rrb_launch_step(e->model->dev, a, stream)) return rr_fail(RR_ECUDA, rrb_error());
+  if (rrb_set_device(e->device) || rrb_launch_step(rr_env_dev(e), a, stream)) return rr_fail(RR_ECUDA, rrb_error());
   g_rr_launches++;
   return RR_OK;
 }
@@ -277,7 +288,7 @@ extern "C" int rr_env_step(rr_env *e, const rr_buffers *b, const float *action, 
   RRStepArgs a;
   int rc = rr_fill_args(e, b, action, n_frames, RR_MODE_STEP, a);
   if (rc) return rc;
-  if (rrb_set_device(e->device) || rrb_launch_step(e->model->dev, a, stream)) return rr_fail(RR_ECUDA, rrb_error());
+  if (rrb_set_device(e->device) || rrb_launch_step(rr_env_dev(e), a, stream)) return rr_fail(RR_ECUDA, rrb_error());
   g_rr_launches++;
   return RR_OK;
 }

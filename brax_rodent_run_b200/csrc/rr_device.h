@@ -103,7 +103,7 @@ struct RRStepArgs {
   float *steps, *truncation; /* [B] */
   const float *first_qpos, *first_qvel, *first_act, *first_warm, *first_time, *first_obs;
   /* optional extra outputs of the last forward pass (null = skip) */
-  float *xpos, *xquat, *subtree_com, *qfrc_actuator, *cinert, *cvel, *contact_dist, *qacc;
+  float *xpos, *xquat, *subtree_com, *qfrc_actuator, *cinert, *cvel, *contact_dist, *qacc, *contact_pos, *contact_frame;
   int *niter; /* [B] solver iterations executed in the last substep */
   float *work;          /* [B] clock cycles spent on this environment (load-balancing hint) or null */
   const int *env_order; /* [slots] slot -> env (-1 idle) or null */

@@ -45,8 +45,12 @@
 
 /* CTA-wide rendezvous used only to keep the warps of a CTA in the same code region (instruction-cache locality);
  * it carries no data dependence.  No-op in the host emulator. */
+/* Live warps (substep) and padding warps (substep_idle) reach the rendezvous from different call sites under a condition
+ * that varies per warp.  PTX defines `bar.sync 0` by arrival COUNT, wherever the arriving warps are in the program (it only
+ * has to be warp-uniform, which it is: the condition is per warp); the C++ __syncthreads() rule about divergent code does
+ * not cover that, so the barrier is written as the PTX instruction itself. */
 #ifndef RR_CTA_SYNC
-#define RR_CTA_SYNC() __syncthreads()
+#define RR_CTA_SYNC() asm volatile("bar.sync 0;" ::: "memory")
 #endif
 #ifndef RR_DUP_SOLVE
 #define RR_DUP_SOLVE 0
@@ -2087,6 +2091,13 @@ RR_DEV void env_run(const RRModelDev &m, const RRStepArgs &a, int env_in, int sl
   }
   /* optional raw outputs that survive the solver phase */
   if (a.contact_dist && m.nefc) for (int i = lane; i < m.ncon; i += 32) a.contact_dist[e * m.ncon + i] = c.con_dist[i];
+  if (a.contact_pos && m.nefc)
+    for (int i = lane; i < 3 * m.ncon; i += 32) {
+      const int cc = i / 3, k = i - 3 * cc;
+      a.contact_pos[e * 3 * m.ncon + i] = c.cab[12 * cc + 9 + k] + c.com[3 * RI(body_rootslot, RI(pair_body, RI(con_pair, cc))) + k];
+    }
+  if (a.contact_frame && m.nefc)
+    for (int i = lane; i < 9 * m.ncon; i += 32) a.contact_frame[e * 9 * m.ncon + i] = c.cab[12 * (i / 9) + i % 9];
   if (a.qacc) RR_FOR_S { int i = lane + 32 * s; if (i < m.nv) a.qacc[e * m.nv + i] = c.qacc[s]; }
   prof<NS>(c, RR_PROF_EPILOGUE);
   prof_flush<NS>(c);

@@ -59,17 +59,79 @@ class System:
         return self.nbody - 1
 
 
+@dataclasses.dataclass
+class Transform:
+    """brax.base.Transform: position + unit quaternion per link (world frame)."""
+    pos: torch.Tensor
+    rot: torch.Tensor
+
+
+@dataclasses.dataclass
+class Motion:
+    """brax.base.Motion: angular + linear velocity per link, at the link origin (world frame)."""
+    ang: torch.Tensor
+    vel: torch.Tensor
+
+
+@dataclasses.dataclass
+class Contact:
+    """brax.mjx State.contact (mjx.Contact re-typed by brax.mjx.pipeline with link_idx).  One row per
+    static candidate contact (capsule pairs first, two each; then sphere / ellipsoid pairs); dist < 0 = penetrating."""
+    dist: torch.Tensor          # [B, ncon]
+    pos: torch.Tensor           # [B, ncon, 3]
+    frame: torch.Tensor         # [B, ncon, 3, 3] rows: normal, tangent 1, tangent 2
+    includemargin: torch.Tensor  # [ncon]
+    friction: torch.Tensor      # [ncon, 5] (sliding x2, torsional, rolling x2 -- MuJoCo's contact friction layout)
+    solref: torch.Tensor        # [ncon, 2]
+    solimp: torch.Tensor        # [ncon, 5]
+    geom1: torch.Tensor         # [ncon] int
+    geom2: torch.Tensor         # [ncon] int
+    link_idx: Tuple[torch.Tensor, torch.Tensor]  # body(geom) - 1 (-1 = world), as brax
+    elasticity: torch.Tensor    # [ncon] zeros (brax fills zeros for mjx)
+
+
 class PipelineState:
     """The fields of mjx.Data / brax.mjx.State the reference reads (Rodent_Env_Brax.py:110-162,
     brax_rodent_run_ppo.py:155).  cinert / cvel / qfrc_actuator are views reconstructed from the
     observation the kernel wrote, so no extra HBM traffic is spent on them."""
 
     def __init__(self, env: "Rodent", qpos, qvel, act, qacc_warmstart, time, ctrl, obs=None, xpos=None, xquat=None,
-                 subtree_com=None, contact_dist=None):
+                 subtree_com=None, contact_dist=None, contact_pos=None, contact_frame=None):
         self._env = env
         self.qpos, self.qvel, self.act, self.qacc_warmstart, self.time, self.ctrl = qpos, qvel, act, qacc_warmstart, time, ctrl
         self._obs = obs
         self.xpos, self.xquat, self.subtree_com, self.contact_dist = xpos, xquat, subtree_com, contact_dist
+        self._contact_pos, self._contact_frame = contact_pos, contact_frame
+
+    # brax.mjx.State views (brax.mjx.pipeline.step, SURVEY Appendix B.9) ------------------------------------------------
+    @property
+    def x(self) -> Transform:
+        """Link transforms: x = Transform(xpos[1:], xquat[1:])."""
+        if self.xquat is None:
+            raise AttributeError("x needs kinematics outputs (Rodent(..., kinematics_outputs=True))")
+        return Transform(pos=self.xpos[:, 1:], rot=self.xquat[:, 1:])
+
+    @property
+    def xd(self) -> Motion:
+        """Link velocities at the link origins: cvel[1:] (ang, lin about the tree's subtree COM) moved by
+        offset = xpos[1:] - subtree_com[root]: vel = lin - offset x ang (brax: Transform.create(pos=offset).do(Motion))."""
+        if self.xquat is None:
+            raise AttributeError("xd needs kinematics outputs (Rodent(..., kinematics_outputs=True))")
+        cv = self.cvel[:, 1:]
+        root = self._env._body_rootslot[1:]
+        offset = self.xpos[:, 1:] - self.subtree_com[:, root]
+        ang, lin = cv[..., :3], cv[..., 3:]
+        return Motion(ang=ang, vel=lin - torch.linalg.cross(offset, ang))
+
+    @property
+    def contact(self) -> Contact:
+        if self.contact_dist is None:
+            raise AttributeError("contact needs kinematics outputs (Rodent(..., kinematics_outputs=True))")
+        c = self._env._contact_const
+        B, n = self.contact_dist.shape
+        return Contact(dist=self.contact_dist, pos=self._contact_pos, frame=self._contact_frame.reshape(B, n, 3, 3),
+                       includemargin=c["includemargin"], friction=c["friction"], solref=c["solref"], solimp=c["solimp"],
+                       geom1=c["geom1"], geom2=c["geom2"], link_idx=c["link_idx"], elasticity=c["elasticity"])
 
     # brax aliases
     @property
@@ -217,6 +279,7 @@ class Rodent:
             self._healthy_z_range[0], self._healthy_z_range[1], int(self._terminate_when_unhealthy)))
         self._episode_length = 0
         self._qpos0 = torch.from_numpy(self.sys.qpos0).to(self.device)
+        self._init_views(flat)
         # load balancing: the warps of a CTA rendezvous every substep, so environments of similar cost (last step's
         # cycle count) are grouped into the same CTA and the groups dealt to the CTAs in snake order
         g, w, p = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
@@ -224,6 +287,36 @@ class Rodent:
         self._geometry = (g.value, w.value, p.value)
         self._balance = bool(balance) and self.num_envs > w.value
         self._slot_of_group = self._snake_slots() if self._balance else None
+
+    def _init_views(self, flat: mjcf.FlatModel) -> None:
+        """Constants of the brax.mjx State views (x / xd / contact)."""
+        dev = self.device
+        roots, slot = [], np.zeros(flat.nbody, np.int64)
+        for b in range(1, flat.nbody):  # slot = order of first appearance of the tree root (as csrc/rr_model_build.h)
+            r = int(flat.body_rootid[b])
+            if r not in roots:
+                roots.append(r)
+            slot[b] = roots.index(r)
+        self._body_rootslot = torch.from_numpy(slot).to(dev)
+        npair = int(flat.npair)
+        conadr = np.asarray(flat.pair_conadr, np.int64)
+        cnt = np.diff(np.append(conadr, flat.ncon)) if npair else np.zeros(0, np.int64)
+        con_pair = np.repeat(np.arange(npair), cnt)
+        g1, g2 = np.asarray(flat.pair_geom1, np.int64)[con_pair], np.asarray(flat.pair_geom2, np.int64)[con_pair]
+        gb = np.asarray(flat.geom_bodyid, np.int64)
+        fr = np.asarray(flat.pair_friction, np.float32).reshape(npair, -1)[con_pair] if npair else np.zeros((0, 1), np.float32)
+        gf1, gf2 = np.asarray(flat.geom_friction, np.float32)[g1], np.asarray(flat.geom_friction, np.float32)[g2]
+        pr1, pr2 = np.asarray(flat.geom_priority)[g1], np.asarray(flat.geom_priority)[g2]
+        f3 = np.where((pr1 > pr2)[:, None], gf1, np.where((pr2 > pr1)[:, None], gf2, np.maximum(gf1, gf2)))  # MuJoCo mixing rule
+        friction = np.stack([fr[:, 0], fr[:, 0], f3[:, 1], f3[:, 2], f3[:, 2]], 1) if npair else np.zeros((0, 5), np.float32)
+        tt = lambda a, dt=torch.float32: torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device=dev)
+        self._contact_const = dict(
+            includemargin=tt(np.asarray(flat.pair_includemargin, np.float32)[con_pair]), friction=tt(friction),
+            solref=tt(np.asarray(flat.pair_solref, np.float32).reshape(npair, 2)[con_pair]),
+            solimp=tt(np.asarray(flat.pair_solimp, np.float32).reshape(npair, 5)[con_pair]),
+            geom1=tt(g1, torch.int64), geom2=tt(g2, torch.int64),
+            link_idx=(tt(gb[g1] - 1, torch.int64), tt(gb[g2] - 1, torch.int64)),
+            elasticity=torch.zeros(len(con_pair), device=dev))
 
     def _snake_slots(self) -> torch.Tensor:
         """Slot filled by the k-th most expensive environment.  Environments of similar cost share a CTA pass (the warps
@@ -308,6 +401,9 @@ class Rodent:
                  obs=self._empty(B, d.obs_dim), reward=self._empty(B), done=self._empty(B), metrics=self._empty(B, 3))
         if self._kin:
             t.update(xpos=self._empty(B, d.nbody, 3), xquat=self._empty(B, d.nbody, 4), subtree_com=self._empty(B, d.nroot, 3))
+            if d.ncon > 0:
+                t.update(contact_dist=self._empty(B, d.ncon), contact_pos=self._empty(B, d.ncon, 3),
+                         contact_frame=self._empty(B, d.ncon, 9))
         if self._episode_length:
             t.update(steps=self._empty(B), truncation=self._empty(B))
         if self._balance:
@@ -319,7 +415,9 @@ class Rodent:
 
     def _make_state(self, t, ctrl, info) -> State:
         ps = PipelineState(self, t["qpos"], t["qvel"], t["act"], t["qacc_warmstart"], t["time"], ctrl, obs=t["obs"],
-                           xpos=t.get("xpos"), xquat=t.get("xquat"), subtree_com=t.get("subtree_com"))
+                           xpos=t.get("xpos"), xquat=t.get("xquat"), subtree_com=t.get("subtree_com"),
+                           contact_dist=t.get("contact_dist"), contact_pos=t.get("contact_pos"),
+                           contact_frame=t.get("contact_frame"))
         m = t["metrics"]
         metrics = {"pos_reward": m[:, 0], "reward_quadctrl": m[:, 1], "reward_alive": m[:, 2]}
         return State(ps, t["obs"], t["reward"], t["done"], metrics, info)

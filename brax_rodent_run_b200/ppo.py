@@ -473,40 +473,79 @@ class PPO:
         self._graph, self._graph_warm = None, 0
 
 
+def policy_from_brax_params(params, device, deterministic: bool = False, generator: Optional[torch.Generator] = None):
+    """brax `make_policy(params, deterministic)` (ppo_networks.make_inference_fn) for a `(normalizer, policy)` parameter tuple
+    as pickled by brax model.save_params / returned by PPO.export_brax_params: returns policy(obs, rng=None) -> (action, extras)
+    with the observation normalised by (mean, std) and a swish MLP in flax naming.  Independent of any PPO instance, so a
+    callback can evaluate a checkpoint while training goes on (brax_rodent_run_ppo.py:135-151)."""
+    norm, pol = params[0], params[1]
+    get = (lambda k: norm.get(k)) if isinstance(norm, dict) else (lambda k: getattr(norm, k, None))
+    as_t = lambda x: torch.as_tensor(np.asarray(x), dtype=torch.float32, device=device)
+    mean, std = as_t(get("mean")), as_t(get("std"))
+    layers = pol["params"] if "params" in pol else pol
+    ws = [(as_t(layers[f"hidden_{i}"]["kernel"]), as_t(layers[f"hidden_{i}"]["bias"])) for i in range(len(layers))]
+
+    @torch.no_grad()
+    def policy(obs, rng=None):
+        h = (obs.to(device, torch.float32) - mean) / std
+        for i, (w, b) in enumerate(ws):
+            h = h @ w + b
+            if i + 1 < len(ws):
+                h = F.silu(h)
+        if deterministic:
+            loc = h.chunk(2, dim=-1)[0]
+            return torch.tanh(loc), {"log_prob": torch.zeros(obs.shape[0], device=device), "raw_action": loc}
+        gen = rng if isinstance(rng, torch.Generator) else generator
+        action, raw, lp = tanh_normal_sample(h, gen)
+        return action, {"log_prob": lp, "raw_action": raw}
+
+    return policy
+
+
 def train(environment: Rodent, cfg: PPOConfig, progress_fn: Callable[[int, Dict], None] = lambda *a: None,
           policy_params_fn: Callable = lambda *a: None, eval_env: Optional[Rodent] = None):
     """ppo.train(environment=env, progress_fn=..., policy_params_fn=...) (brax_rodent_run_ppo.py:200-202).
-    Returns (make_inference_fn, params, metrics) like brax."""
+    Returns (make_inference_fn, params, metrics) like brax.
+
+    Schedule as brax.training.agents.ppo.train: `num_evals_after_init = max(num_evals - 1, 1)` epochs of
+    `ceil(num_timesteps / (num_evals_after_init * env_steps_per_training_step))` training steps, each epoch followed by
+    evaluation, progress_fn(num_steps, metrics) and policy_params_fn(num_steps, make_policy, params); with num_evals > 1 the
+    untrained policy is evaluated first (progress_fn(0, ...)).  `make_policy(params, deterministic=False)` is brax's
+    make_inference_fn: called with the `params` handed to the callback (or any exported tuple) it builds a stand-alone
+    policy; called without arguments it acts with the live agent."""
     agent = PPO(environment.wrap_for_training(cfg.episode_length), cfg)
     steps_per_train = cfg.batch_size * cfg.num_minibatches * cfg.unroll_length * agent.world
-    num_train = max(1, -(-cfg.num_timesteps // steps_per_train))
-    per_eval = max(1, num_train // max(cfg.num_evals, 1))
+    evals_after_init = max(cfg.num_evals - 1, 1)
+    per_epoch = max(1, -(-cfg.num_timesteps // (evals_after_init * steps_per_train)))
     state = environment.reset(cfg.seed + agent.rank)
     metrics: Dict[str, float] = {}
+
+    def make_inference_fn(params=None, deterministic=False):
+        if params is not None and not isinstance(params, PPO):
+            return policy_from_brax_params(params, agent.device, deterministic, agent.gen)
+
+        def policy(obs, rng=None):
+            action, raw, lp = agent.act(obs, deterministic)
+            return action, {"log_prob": lp, "raw_action": raw}
+        return policy
+
     if eval_env is not None and cfg.num_evals > 1:  # brax evaluates the untrained policy first (`num_evals` counts it)
         m0 = agent.evaluate(eval_env)
         if agent.rank == 0:
             progress_fn(0, m0)
     t0 = time.time()
-    for it in range(num_train):
-        state, m = agent.training_step(state)
-        if (it + 1) % per_eval == 0 or it == num_train - 1:
-            if agent.device.type == "cuda":
-                torch.cuda.synchronize(agent.device)
-            metrics = {f"training/{k}": float(v) for k, v in m.items()}
-            metrics["training/sps"] = agent.env_steps / (time.time() - t0)
-            metrics["training/walltime"] = time.time() - t0
-            if eval_env is not None:
-                metrics.update(agent.evaluate(eval_env))
-            if agent.rank == 0:
-                progress_fn(agent.env_steps, metrics)
-                policy_params_fn(agent.env_steps, agent.make_inference_fn if hasattr(agent, "make_inference_fn") else None,
-                                 agent.export_brax_params())
-
-    def make_inference_fn(params=None, deterministic=False):
-        def policy(obs, rng=None):
-            action, raw, lp = agent.act(obs, deterministic)
-            return action, {"log_prob": lp, "raw_action": raw}
-        return policy
+    for epoch in range(evals_after_init):
+        for _ in range(per_epoch):
+            state, m = agent.training_step(state)
+        if agent.device.type == "cuda":
+            torch.cuda.synchronize(agent.device)
+        metrics = {f"training/{k}": float(v) for k, v in m.items()}
+        metrics["training/sps"] = agent.env_steps / (time.time() - t0)
+        metrics["training/walltime"] = time.time() - t0
+        if eval_env is not None:
+            metrics.update(agent.evaluate(eval_env))
+        if agent.rank == 0:
+            progress_fn(agent.env_steps, metrics)
+            policy_params_fn(agent.env_steps, make_inference_fn, agent.export_brax_params())
 
     return make_inference_fn, agent, metrics

@@ -75,6 +75,9 @@ typedef struct rr_buffers {
    * Rodent._balance) shortens the wait.  Null = identity order. */
   float *work;
   const int32_t *env_order;
+  /* contact views of the last forward pass (brax.mjx State.contact: torchrl_explore.ipynb:609-618), optional */
+  float *contact_pos;     /* [B, ncon, 3] world */
+  float *contact_frame;   /* [B, ncon, 3, 3] rows = normal, tangent 1, tangent 2 */
 } rr_buffers;
 
 const char *rr_last_error(void);

@@ -67,9 +67,14 @@ static void run_warp(void (*body)(int, void *), void *arg) {
     g_done[l] = false;
     g_par[l] = 0;
   }
+  /* RR_EMU_LANE_ORDER=reverse|odd-first runs the lanes of every scheduling round in another order: a hazard between lanes
+   * that is not separated by a warp primitive (the class of bug racecheck finds) then changes the result */
+  const char *ord = getenv("RR_EMU_LANE_ORDER");
+  const int mode = !ord ? 0 : (ord[0] == 'r' ? 1 : 2);
   for (;;) {
     int alive = 0;
-    for (int l = 0; l < NL; l++) {
+    for (int k = 0; k < NL; k++) {
+      const int l = mode == 0 ? k : (mode == 1 ? NL - 1 - k : (k < NL / 2 ? 2 * k + 1 : 2 * (k - NL / 2)));
       if (g_done[l]) continue;
       g_lane = l;
       swapcontext(&g_sched, &g_fib[l]);

@@ -73,3 +73,30 @@ def test_balanced_order_is_bitwise_neutral():
         outs.append(rollout(env, sf, nq_, nv_, acts))
     for k in outs[0]:
         assert np.array_equal(outs[0][k], outs[1][k]), k
+
+
+def test_emulator_lane_order_independence(emu_lib, make_env, monkeypatch):
+    """Race check on the host (compute-sanitizer is closed on the GPU pool, profiles/r02_sanitizer_closed.txt): the fiber
+    emulator runs the 32 lanes of a warp round-robin between warp primitives; running them in reverse and in odd-first order
+    must give bit-identical results.  A shared-memory hazard between lanes that no __syncwarp / shuffle / ballot separates
+    shows up as a difference (the emulator also poisons shared memory with NaN before every environment)."""
+    import os
+    m = load_asset("rodent_0")
+    rng = np.random.default_rng(3)
+    B = 2
+    sf, nq_, nv_ = rng.integers(0, 100, B), rng.uniform(-.01, .01, (B, m.nq)), rng.uniform(-.01, .01, (B, m.nv))
+    act = rng.uniform(-1, 1, (2, B, m.nu)).astype(np.float32)
+    outs = []
+    for order in (None, "reverse", "odd-first"):
+        if order is None:
+            monkeypatch.delenv("RR_EMU_LANE_ORDER", raising=False)
+        else:
+            monkeypatch.setenv("RR_EMU_LANE_ORDER", order)
+        env = make_env("emu", synthetic_track(), num_envs=B, model=m, iterations=4, ls_iterations=4, n_frames=3).wrap_for_training(1000)
+        st = env.reset_from(torch.tensor(sf), torch.tensor(nq_), torch.tensor(nv_))
+        for t in range(2):
+            st = env.step(st, torch.tensor(act[t]))
+        outs.append((st.obs.numpy().copy(), st.pipeline_state.qpos.numpy().copy(), st.pipeline_state.qacc_warmstart.numpy().copy()))
+    for o in outs[1:]:
+        for a, b in zip(outs[0], o):
+            assert np.array_equal(a, b)

@@ -229,3 +229,102 @@ def test_fused_loss_matches_autograd_on_gpu():
     env = Rodent(synthetic_track(), num_envs=2, device="cuda:0", model=load_asset("rodent_0"), iterations=1, ls_iterations=1, n_frames=1)
     agent, mb = _loss_case(env, "cuda:0", seed=1, T=10, B=512)
     _compare_fused_with_autograd(agent, mb, 2e-4)
+
+
+class _BraxRunningStatisticsState:
+    """Shape of brax.training.acme.running_statistics.RunningStatisticsState (a flax struct: attribute access, not a dict),
+    as unpickled from a brax `model.save_params` file (brax_rodent_run_ppo.py:204-206, render_rollout.ipynb:117-118)."""
+
+    def __init__(self, count, mean, summed_variance, std):
+        self.count, self.mean, self.summed_variance, self.std = count, mean, summed_variance, std
+
+
+def _brax_style_params(obs, act, hidden, seed):
+    """A `(normalizer, policy)` tuple with brax's real structure: RunningStatisticsState-like object + flax param tree
+    {"params": {"hidden_i": {"kernel": [in, out], "bias": [out]}}}, numpy leaves."""
+    rng = np.random.default_rng(seed)
+    sizes = (obs,) + tuple(hidden) + (2 * act,)
+    tree = {"params": {f"hidden_{i}": {"kernel": rng.normal(0, 0.1, (sizes[i], sizes[i + 1])).astype(np.float32),
+                                       "bias": rng.normal(0, 0.1, sizes[i + 1]).astype(np.float32)} for i in range(len(sizes) - 1)}}
+    std = rng.uniform(0.5, 2.0, obs).astype(np.float32)
+    norm = _BraxRunningStatisticsState(np.float32(1000.0), rng.normal(0, 1, obs).astype(np.float32), (std ** 2) * 1000.0, std)
+    return norm, tree
+
+
+def test_import_brax_structured_pickle_fixture(emu_lib, tmp_path):
+    """A brax-structured checkpoint (object normaliser + flax tree, through pickle) drives the policy exactly as its own
+    numpy forward pass: swish MLP on (obs - mean) / std, action = tanh(loc)."""
+    import pickle
+    from brax_rodent_run_b200 import ppo
+    cfg = ppo.PPOConfig(**TINY)
+    env = tiny_env(emu_lib).wrap_for_training(cfg.episode_length)
+    params = _brax_style_params(env.observation_size, env.action_size, cfg.policy_hidden, 3)
+    path = tmp_path / "brax_params.pkl"
+    path.write_bytes(pickle.dumps(params))
+    loaded = pickle.loads(path.read_bytes())
+    agent = ppo.PPO(env, cfg)
+    agent.import_brax_params(loaded)
+    state = env.reset(1)
+    obs = state.obs.numpy().astype(np.float64)
+    h = (obs - params[0].mean) / params[0].std
+    layers = params[1]["params"]
+    for i in range(len(layers)):
+        h = h @ layers[f"hidden_{i}"]["kernel"] + layers[f"hidden_{i}"]["bias"]
+        if i + 1 < len(layers):
+            h = h / (1 + np.exp(-h))
+    want = np.tanh(h[:, :env.action_size])
+    got, _, _ = agent.act(state.obs, deterministic=True)
+    assert np.abs(got.numpy() - want).max() < 1e-5
+    # the stand-alone make_policy(params, deterministic=True) of the training callback gives the same action
+    pol = ppo.policy_from_brax_params(loaded, "cpu", deterministic=True)
+    a2, extras = pol(state.obs, None)
+    assert np.abs(a2.numpy() - want).max() < 1e-5 and set(extras) == {"log_prob", "raw_action"}
+
+
+def test_train_callback_gets_make_policy_like_brax(emu_lib):
+    """policy_params_fn(num_steps, make_policy, params) as the reference uses it (brax_rodent_run_ppo.py:135-151):
+    make_policy(params, deterministic=True) -> inference_fn(obs, rng) -> (ctrl, extras); brax's evaluation cadence."""
+    from brax_rodent_run_b200 import ppo
+    cfg = ppo.PPOConfig(**dict(TINY, num_timesteps=48, num_evals=3))
+    env = tiny_env(emu_lib)
+    eval_env = tiny_env(emu_lib).wrap_for_training(cfg.episode_length)
+    calls, progress = [], []
+
+    def policy_params_fn(num_steps, make_policy, params):
+        inference_fn = make_policy(params, deterministic=True)
+        st = eval_env.reset(0)
+        ctrl, _ = inference_fn(st.obs, None)
+        st = eval_env.step(st, ctrl)
+        calls.append((num_steps, tuple(ctrl.shape), bool(torch.isfinite(st.obs).all())))
+
+    make_inference_fn, agent, metrics = ppo.train(env, cfg, progress_fn=lambda n, m: progress.append(n),
+                                                  policy_params_fn=policy_params_fn, eval_env=eval_env)
+    per_train = cfg.batch_size * cfg.num_minibatches * cfg.unroll_length
+    # num_evals = 3 -> the untrained evaluation + 2 epochs of ceil(48 / (2 * 8)) = 3 training steps
+    assert progress == [0, 3 * per_train, 6 * per_train]
+    assert [c[0] for c in calls] == [3 * per_train, 6 * per_train] and all(c[1] == (2, env.action_size) and c[2] for c in calls)
+    live = make_inference_fn()  # no params: the live agent
+    a, extras = live(eval_env.reset(0).obs)
+    assert a.shape == (2, env.action_size)
+
+
+def test_resume_is_bitwise(emu_lib):
+    """Checkpoint / resume: state_dict -> load_state_dict into a fresh agent (same generator state, same env state) continues
+    bit-for-bit: the next training step gives identical parameters and losses."""
+    import copy
+    from brax_rodent_run_b200.ppo import PPO, PPOConfig
+    cfg = PPOConfig(**dict(TINY, normalize_observations=False))
+    env = tiny_env(emu_lib).wrap_for_training(cfg.episode_length)
+    a = PPO(env, cfg)
+    state = env.reset(0)
+    state, _ = a.training_step(state)
+    ckpt = copy.deepcopy(a.state_dict())
+    gen_state = a.gen.get_state()
+    b = PPO(env, cfg)
+    b.load_state_dict(ckpt)
+    b.gen.set_state(gen_state)
+    s1, m1 = a.training_step(state)
+    s2, m2 = b.training_step(state)
+    for p, q in zip(a.params, b.params):
+        assert torch.equal(p, q)
+    assert torch.equal(s1.obs, s2.obs) and all(float(m1[k]) == float(m2[k]) for k in m1)
