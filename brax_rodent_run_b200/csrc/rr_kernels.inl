@@ -1651,7 +1651,7 @@ RR_DEV void solve_constraints(Ctx<NS> &c) {
   const float nvf = (float)(m.nv > 1 ? m.nv : 1);
   const float scale = 1.f / (m.meaninertia * nvf);
   float Ma[NS], grad[NS], Mgrad[NS], search[NS], mv[NS];
-  float gauss = 0.f, cost = INFINITY, prev_cost = INFINITY, beta = 0.f;
+  float gauss = 0.f, cost = INFINITY, prev_cost = INFINITY, beta = 0.f, gg = 0.f;
   RR_FOR_S mv[s] = 0.f;
   int niter = 0;
   bool first = true, finished = false;
@@ -1687,7 +1687,7 @@ RR_DEV void solve_constraints(Ctx<NS> &c) {
     if (!finished && !first) {
       if (m.iterations != 1) {
         float improvement = (prev_cost - cost) * scale;
-        float gradient = RR_SQRT(vdot<NS>(grad, grad)) * scale;
+        float gradient = RR_SQRT(gg) * scale; /* gg = grad . grad, reduced together with the Polak-Ribiere sums */
         if (niter >= m.iterations || improvement < m.tolerance || gradient < m.tolerance) finished = true;
       } else if (niter >= 1) {
         finished = true;
@@ -1695,8 +1695,6 @@ RR_DEV void solve_constraints(Ctx<NS> &c) {
     }
     if (!finished && !first) {
       /* ---- linesearch ---- */
-      float smag = RR_SQRT(vdot<NS>(search, search)) * m.meaninertia * nvf;
-      float gtol = m.tolerance * m.ls_tolerance * smag;
       /* mv = M search.  search = -Mgrad + beta search_prev with M Mgrad = grad (Mgrad is the LD solve of grad), so
        * mv = -grad + beta mv_prev: the same vector MJX gets from mul_m(search), without the product. */
 #if RR_MV_RECURRENCE
@@ -1711,14 +1709,16 @@ RR_DEV void solve_constraints(Ctx<NS> &c) {
 #pragma unroll 1
       for (int rep = 0; rep <= RR_DUP_MULJ; rep++) mul_j<NS>(c, c.row_jv);
       prof<NS>(c, RR_PROF_LS_MULJ);
-      float g0 = gauss, g1 = 0.f, g2 = 0.f;
-      RR_FOR_S { g1 += search[s] * (Ma[s] - c.qfrc_smooth[s]); g2 += search[s] * mv[s]; }
+      float g0 = gauss, g1 = 0.f, g2 = 0.f, ss = 0.f; /* one reduction for the Gauss quadratic and |search|^2 */
+      RR_FOR_S { g1 += search[s] * (Ma[s] - c.qfrc_smooth[s]); g2 += search[s] * mv[s]; ss += search[s] * search[s]; }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
         g1 += __shfl_xor_sync(RR_FULL, g1, o);
         g2 += __shfl_xor_sync(RR_FULL, g2, o);
+        ss += __shfl_xor_sync(RR_FULL, ss, o);
       }
       g2 *= 0.5f;
+      const float gtol = m.tolerance * m.ls_tolerance * (RR_SQRT(ss) * m.meaninertia * nvf);
       LSPoint p0, lo, hi;
       {
         float a1[1] = {0.f};
@@ -1777,26 +1777,37 @@ RR_DEV void solve_constraints(Ctx<NS> &c) {
     for (int rep = 0; rep <= RR_DUP_MULJT; rep++) mul_jt<NS>(c, c.row_jv, c.qfrc_constraint);
     prof<NS>(c, RR_PROF_CRB); /* profiling bucket "crb" = constraint_cost + J' f inside the solver */
     RR_FOR_S { grad[s] = Ma[s] - c.qfrc_smooth[s] - c.qfrc_constraint[s]; }
+    if (trip == m.iterations && !first) {
+      /* the last gradient update the iteration limit allows: M^-1 grad and the next search direction would never be used
+       * (MJX computes and discards them); qfrc_constraint above is what the integrator needs */
+      niter++;
+      continue;
+    }
 #pragma unroll 1
     for (int rep = 0; rep <= RR_DUP_SOLVE; rep++) {
       RR_FOR_S Mgrad[s] = grad[s];
       solve_ld<NS>(c, Mgrad, c.LD, c.dinv);
     }
     prof<NS>(c, RR_PROF_VEL); /* profiling bucket "com_vel" = the M^-1 grad solve inside the solver */
-    if (first) {
-      RR_FOR_S search[s] = -Mgrad[s];
-      first = false;
-    } else {
+    {
       float num = 0.f, den = 0.f;
-      RR_FOR_S { num += grad[s] * (Mgrad[s] - prev_Mgrad[s]); den += prev_grad[s] * prev_Mgrad[s]; }
+      gg = 0.f;
+      RR_FOR_S { gg += grad[s] * grad[s]; }
+      if (!first) RR_FOR_S { num += grad[s] * (Mgrad[s] - prev_Mgrad[s]); den += prev_grad[s] * prev_Mgrad[s]; }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
         num += __shfl_xor_sync(RR_FULL, num, o);
         den += __shfl_xor_sync(RR_FULL, den, o);
+        gg += __shfl_xor_sync(RR_FULL, gg, o);
       }
-      beta = fmaxf(0.f, num * RR_RCP(fmaxf(RR_MINVAL, den)));
-      RR_FOR_S search[s] = -Mgrad[s] + beta * search[s];
-      niter++;
+      if (first) {
+        RR_FOR_S search[s] = -Mgrad[s];
+        first = false;
+      } else {
+        beta = fmaxf(0.f, num * RR_RCP(fmaxf(RR_MINVAL, den)));
+        RR_FOR_S search[s] = -Mgrad[s] + beta * search[s];
+        niter++;
+      }
     }
     prof<NS>(c, RR_PROF_SOLVE_UPD);
   }
