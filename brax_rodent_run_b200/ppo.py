@@ -53,6 +53,7 @@ class PPOConfig:
     seed: int = 0
     fused_loss: bool = True         # loss + gradient w.r.t. the network outputs in two hand-written kernels (rr_ppo_loss)
     cuda_graph: bool = True         # replay the minibatch update (loss, backward, Adam) as one CUDA graph on CUDA devices
+    rollout_graph: bool = True      # replay the unroll (unroll_length x [policy MLP + sample + env step]) as one CUDA graph
     tf32: bool = True               # TF32 tensor-core matmuls, as XLA's default float32 dot precision on NVIDIA GPUs
     policy_hidden: tuple = (32, 32, 32, 32)
     value_hidden: tuple = (256, 256, 256, 256, 256)
@@ -96,9 +97,11 @@ class RunningStats:
         s2 = (diff_old * (batch - mean)).sum(0)
         if distributed:
             dist.all_reduce(s2)
-        self.summed_variance = self.summed_variance + s2
-        self.count, self.mean = count, mean
-        self.std = torch.sqrt((self.summed_variance / count.float()).clamp_min(0.0)).clamp(std_min, std_max)
+        # in place: the captured rollout graph reads mean / std at fixed addresses
+        self.summed_variance.add_(s2)
+        self.count.copy_(count)
+        self.mean.copy_(mean)
+        self.std.copy_(torch.sqrt((self.summed_variance / count.float()).clamp_min(0.0)).clamp(std_min, std_max))
 
     def normalize(self, x: torch.Tensor) -> torch.Tensor:
         return (x - self.mean) / self.std
@@ -107,17 +110,20 @@ class RunningStats:
         return dict(count=self.count, mean=self.mean, summed_variance=self.summed_variance, std=self.std)
 
     def load_state_dict(self, d):
-        self.count, self.mean, self.summed_variance, self.std = d["count"], d["mean"], d["summed_variance"], d["std"]
+        for k in ("count", "mean", "summed_variance", "std"):
+            getattr(self, k).copy_(torch.as_tensor(d[k], device=self.mean.device))
 
 
 _LOG2 = math.log(2.0)
 
 
-def tanh_normal_sample(logits: torch.Tensor, gen: Optional[torch.Generator] = None):
-    """NormalTanhDistribution: returns (action, raw_action, log_prob)."""
+def tanh_normal_sample(logits: torch.Tensor, gen: Optional[torch.Generator] = None, eps: Optional[torch.Tensor] = None):
+    """NormalTanhDistribution: returns (action, raw_action, log_prob).  `eps`: pre-drawn standard normal noise (the captured
+    rollout graph draws it outside the graph)."""
     loc, scale = logits.chunk(2, dim=-1)
     scale = F.softplus(scale) + 1e-3
-    eps = torch.randn(loc.shape, device=loc.device, generator=gen)
+    if eps is None:
+        eps = torch.randn(loc.shape, device=loc.device, generator=gen)
     raw = loc + scale * eps
     return torch.tanh(raw), raw, tanh_normal_log_prob(logits, raw)
 
@@ -228,6 +234,8 @@ class PPO:
         cuda = self.device.type == "cuda"
         self.opt = torch.optim.Adam(self.params, lr=cfg.learning_rate, eps=1e-8, capturable=self._use_graph,
                                     fused=True if cuda else None)  # one multi-tensor kernel instead of ~15 foreach launches
+        self._use_rollout_graph = bool(cfg.rollout_graph) and self.device.type == "cuda"
+        self._rg = None             # captured unroll (policy + sample + env step) x unroll_length
         self._graph = None          # (fwd + bwd [+ Adam]) graph, static minibatch buffers, static metrics
         self._graph_warm = 0
         self.normalizer = RunningStats(obs, self.device)
@@ -246,20 +254,75 @@ class PPO:
         return obs if getattr(self, "_batch_is_normalized", False) else self._norm(obs)
 
     @torch.no_grad()
-    def act(self, obs, deterministic=False):
+    def act(self, obs, deterministic=False, eps=None):
         logits = self.policy(self._norm(obs))
         if deterministic:
             loc = logits.chunk(2, dim=-1)[0]
             return torch.tanh(loc), loc, torch.zeros(obs.shape[0], device=obs.device)
-        return tanh_normal_sample(logits, self.gen)
+        return tanh_normal_sample(logits, self.gen, eps)
 
     @torch.no_grad()
     def unroll(self, state: State):
-        """acting.generate_unroll: `unroll_length` policy + env steps; returns (state, transitions time-major)."""
+        """acting.generate_unroll: `unroll_length` policy + env steps; returns (state, transitions time-major).  On CUDA the
+        whole unroll is captured once as a CUDA graph and replayed (cfg.rollout_graph)."""
+        if self._use_rollout_graph:
+            return self._unroll_graphed(state)
+        return self._unroll_eager(state, None)
+
+    # fields of the carried State that the captured unroll reads at fixed addresses
+    _PS_FIELDS = ("qpos", "qvel", "act", "qacc_warmstart", "time")
+
+    def _state_tensors(self, state: State):
+        ps = state.pipeline_state
+        out = [getattr(ps, k) for k in self._PS_FIELDS] + [state.obs, state.reward, state.done, state.info["cur_frame"]]
+        out += [state.info[k] for k in ("steps", "truncation") if k in state.info]
+        return out
+
+    @torch.no_grad()
+    def _unroll_graphed(self, state: State):
+        """The unroll as ONE CUDA graph: policy MLP + tanh-normal sample + rr_step_kernel, unroll_length times.  The carried
+        State lives in static tensors (the graph ends by copying the final state back into them), the exploration noise is
+        drawn outside the graph from the agent's generator, and the transitions are copied out of the graph's memory after
+        every replay (they are overwritten by the next one).  Same arithmetic as the eager unroll (tests/test_ppo.py)."""
+        T, B, A = self.cfg.unroll_length, self.env.num_envs, self.env.action_size
+        if self._rg is None:
+            # static carried state = clones of the first state handed in (the auto-reset cache first_* is shared, read-only)
+            import copy
+            ps = copy.copy(state.pipeline_state)
+            for k in self._PS_FIELDS:
+                setattr(ps, k, getattr(ps, k).clone())
+            info = dict(state.info)
+            for k in ("cur_frame", "steps", "truncation"):
+                if k in info:
+                    info[k] = info[k].clone()
+            self._rg_state = State(ps, state.obs.clone(), state.reward.clone(), state.done.clone(), dict(state.metrics), info)
+            self._rg_eps = torch.empty((T, B, A), device=self.device)
+            self._rg_eps.normal_(generator=self.gen)
+            side = torch.cuda.Stream(self.device)   # warm-up off the capture stream (allocator, cuBLAS workspaces)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                self._unroll_eager(self._rg_state, self._rg_eps)
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                new_state, data = self._unroll_eager(self._rg_state, self._rg_eps)
+                for dst, src in zip(self._state_tensors(self._rg_state), self._state_tensors(new_state)):
+                    dst.copy_(src)
+            self._rg, self._rg_data = g, data
+        elif state is not self._rg_state:  # a state from elsewhere (e.g. a fresh reset): load it into the static buffers
+            for dst, src in zip(self._state_tensors(self._rg_state), self._state_tensors(state)):
+                dst.copy_(src)
+        self._rg_eps.normal_(generator=self.gen)
+        self._rg.replay()
+        data = {k: v.clone() for k, v in self._rg_data.items()}
+        return self._rg_state, data
+
+    @torch.no_grad()
+    def _unroll_eager(self, state: State, eps_all):
         T = self.cfg.unroll_length
         obs, raw, logp, rew, disc, trunc = [], [], [], [], [], []
-        for _ in range(T):
-            action, raw_a, lp = self.act(state.obs)
+        for t in range(T):
+            action, raw_a, lp = self.act(state.obs, eps=None if eps_all is None else eps_all[t])
             obs.append(state.obs)
             state = self.env.step(state, action)
             raw.append(raw_a); logp.append(lp); rew.append(state.reward)

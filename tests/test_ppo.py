@@ -328,3 +328,32 @@ def test_resume_is_bitwise(emu_lib):
     for p, q in zip(a.params, b.params):
         assert torch.equal(p, q)
     assert torch.equal(s1.obs, s2.obs) and all(float(m1[k]) == float(m2[k]) for k in m1)
+
+
+@pytest.mark.gpu
+def test_rollout_graph_matches_eager_unroll():
+    """The captured unroll (policy MLP + tanh-normal sample + rr_step_kernel, unroll_length times, one CUDA graph) against the
+    eager unroll with the same exploration noise: identical transitions and final state, over two consecutive replays."""
+    from brax_rodent_run_b200.env import Rodent
+    from brax_rodent_run_b200.ppo import PPO, PPOConfig
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    cfg = PPOConfig(num_envs=64, batch_size=64, num_minibatches=2, unroll_length=5, episode_length=7)
+    mk = lambda: Rodent(synthetic_track(), num_envs=64, device="cuda:0", model=load_asset("rodent_0"), iterations=2, ls_iterations=2,
+                        n_frames=2, terminate_when_unhealthy=False, kinematics_outputs=False).wrap_for_training(cfg.episode_length)
+    env_g, env_e = mk(), mk()
+    a_g, a_e = PPO(env_g, cfg), PPO(env_e, PPOConfig(**dict(dataclasses_asdict(cfg), rollout_graph=False)))
+    a_e.policy.load_state_dict(a_g.policy.state_dict())
+    s_g, s_e = env_g.reset(3), env_e.reset(3)
+    for rep in range(3):  # episode_length 7 < 15 steps: the fused auto-reset path is replayed too
+        s_g, d_g = a_g.unroll(s_g)
+        s_e, d_e = a_e._unroll_eager(s_e, a_g._rg_eps)  # same noise as the replay just used
+        for k in d_g:
+            assert torch.equal(d_g[k], d_e[k]), (rep, k)
+        assert torch.equal(s_g.obs, s_e.obs) and torch.equal(s_g.pipeline_state.qpos, s_e.pipeline_state.qpos)
+        assert torch.equal(s_g.info["steps"], s_e.info["steps"])
+
+
+def dataclasses_asdict(cfg):
+    import dataclasses
+    return dataclasses.asdict(cfg)
