@@ -53,6 +53,8 @@ class PPOConfig:
     seed: int = 0
     fused_loss: bool = True         # loss + gradient w.r.t. the network outputs in two hand-written kernels (rr_ppo_loss)
     cuda_graph: bool = True         # replay the minibatch update (loss, backward, Adam) as one CUDA graph on CUDA devices
+    graph_allreduce: bool = False   # several ranks: capture the NCCL all-reduce + Adam in the update graph too.  OFF: with torch 2.11 /
+                                    # NCCL 2.28 the 2-rank capture hung on the B200 box (round 2); the eager all-reduce + Adam path is kept
     rollout_graph: bool = True      # replay the unroll (unroll_length x [policy MLP + sample + env step]) as one CUDA graph
     tf32: bool = True               # TF32 tensor-core matmuls, as XLA's default float32 dot precision on NVIDIA GPUs
     policy_hidden: tuple = (32, 32, 32, 32)
@@ -386,8 +388,9 @@ class PPO:
     def _update_graphed(self, data: Dict[str, torch.Tensor], idx: torch.Tensor):
         """One minibatch update with the loss / backward / Adam kernels replayed as a CUDA graph (the eager update is
         ~150 small launches and host-bound at ~3 ms; the GPU work is ~0.3 ms).  The minibatch is gathered into static
-        buffers, the entropy noise is drawn outside the graph from the agent's generator.  With several ranks the graph
-        ends after backward, the flat gradient bucket is all-reduced eagerly and Adam steps outside the graph."""
+        buffers, the entropy noise is drawn outside the graph from the agent's generator.  With several ranks the NCCL
+        all-reduce of the flat gradient bucket and Adam are captured in the same graph (cfg.graph_allreduce; off: the graph
+        ends after backward and they run eagerly)."""
         cfg = self.cfg
         if self._graph is None:
             self._static = {k: torch.empty((v.shape[0], cfg.batch_size) + tuple(v.shape[2:]) if k != "next_observation_last"
@@ -414,14 +417,16 @@ class PPO:
         if self._graph is None:
             g = torch.cuda.CUDAGraph()
             self.opt.zero_grad(set_to_none=True)
+            in_graph = self.world == 1 or self.cfg.graph_allreduce
             with torch.cuda.graph(g):
                 total, metrics = self.loss(st)
                 total.backward()
-                if self.world == 1:
+                if in_graph:
+                    self._allreduce_grads()  # NCCL all-reduce of the flat bucket, captured with the rest (no-op on one rank)
                     self.opt.step()
-            self._graph, self._graph_metrics = g, metrics
+            self._graph, self._graph_metrics, self._graph_full = g, metrics, in_graph
         self._graph.replay()
-        if self.world > 1:
+        if not self._graph_full:
             self._allreduce_grads()
             self.opt.step()
         return self._graph_metrics
