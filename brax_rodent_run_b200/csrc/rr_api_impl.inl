@@ -159,7 +159,7 @@ extern "C" int rr_env_create(const rr_model *cm, int32_t num_envs, int32_t devic
     delete e;
     return rr_fail(RR_ECUDA, rrb_error());
   }
-  e->scratch_stride = 5 * ((m->dev.nefc + 3) & ~3) + 8 + 6 * ((m->dev.ncon + 3) & ~3); /* rows (5 nefc) + per-contact six-vectors */
+  e->scratch_stride = 5 * ((m->dev.nefc + 3) & ~3) + 8 + 6 * ((m->dev.ncon + 3) & ~3) + 32; /* rows (5 nefc) + per-contact six-vectors + profile sums */
   if (rrb_malloc((void **)&e->d_scratch, (size_t)rrb_num_slots() * e->scratch_stride * sizeof(float))) {
     rrb_free(e->d_action_stage); rrb_free(e->d_ibuf); rrb_free(e->d_fbuf);
     delete e;

@@ -14,7 +14,7 @@
 
 /* integer tables: name, expression for the element count (informative) */
 #define RR_DEV_INT_TABLES(X)                                                                              \
-  X(body_parentid) X(body_eparent) X(body_rootslot) X(body_jntadr) X(body_jntnum) X(body_anc) X(level_adr) X(level_body)              \
+  X(body_eparent) X(body_rootslot) X(body_jntadr) X(body_jntnum) X(body_anc)                                                   \
   X(jnt_type) X(jnt_qposadr) X(jnt_dofadr) X(jnt_bodyid)                                                  \
   X(dof_bodyid) X(dof_depth) X(dof_ndesc) X(dof_rowadr) X(dof_log2w) X(dof_pack) X(dof_cbmask) X(dof_descmask) X(dof_ancmask) X(M_meta)                            \
   X(act_dofadr) X(act_qposadr) X(act_dyntype) X(act_gaintype) X(act_biastype) X(act_ctrllimited)          \
@@ -40,7 +40,7 @@
  *                                      observation slices are written to HBM before the solver in the last substep).
  */
 struct RRSmem {
-  int qpos, qvel, act, ctrl, actdot, com, vbuf, xq1, prof_acc; /* A */
+  int qpos, qvel, act, ctrl, actdot, com, vbuf, xq1; /* A */
   int M, LD;                                               /* B */
   int xpos, xquat, cdof;                                   /* C, live through the Jacobian build */
   int cinert, qfrc_act, cvel, cacc, cfrc, crb, fcrb;       /* C1 */
@@ -52,7 +52,8 @@ struct RRSmem {
 
 struct RRModelDev {
   int nq, nv, nu, na, nbody, njnt, ngeom, nM, npair, ncon, nlimit, nefc, nlevel, nroot, ncb;
-  int nround; /* pointer-doubling rounds of the tree scans: 2^nround >= nlevel - 1; body_anc[k nbody + b] = 2^k-th effective ancestor (0 = world) */
+  int nround; /* pointer-doubling rounds of the tree scans: 2^nround >= nlevel - 1; body_anc = the 2^k-th effective
+                 ancestor (0 = world) of body b as byte (k nbody + b) of the table (four per word, RR_BODY_ANC) */
   int solver, iterations, ls_iterations;
   float timestep, gravity[3], tolerance, ls_tolerance, impratio, meaninertia;
   RRSmem sm;
@@ -109,7 +110,7 @@ struct RRStepArgs {
   const int *env_order; /* [slots] slot -> env (-1 idle) or null */
   RRDebug dbg;
   float *scratch;     /* [warp slots, scratch_stride] global overflow for contact Jacobians / constraint rows */
-  int scratch_stride; /* floats: 5 align4(nefc) + 8 + 6 align4(ncon) */
+  int scratch_stride; /* floats: 5 align4(nefc) + 8 + 6 align4(ncon) + 32 (per-stage cycle sums of the instrumented build) */
   long long *prof; /* [B, RR_NPROF] clock64 deltas or null */
 };
 

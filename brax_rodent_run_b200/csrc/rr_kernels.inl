@@ -38,6 +38,8 @@
 #define RI(name, idx) (c.ti[c.m.o_##name + (idx)])
 #define RF(name, idx) (c.tf[c.m.o_##name + (idx)])
 
+/* body_anc: one byte per (round, body) */
+#define RR_BODY_ANC(idx) ((int)(((unsigned)c.ti[c.m.o_body_anc + ((idx) >> 2)] >> (8 * ((idx) & 3))) & 255u))
 /* packed per-entry metadata of the tree-sparse layout: row | col << 8 | rowadr[col] << 16 */
 #define RR_META_ROW(x) ((x) & 255)
 #define RR_META_COL(x) (((x) >> 8) & 255)
@@ -329,7 +331,7 @@ struct Ctx {
     sm_base = sm;
     grows = a.scratch + (size_t)slot_ * a.scratch_stride;
     xq1 = sm + s.xq1;
-    prof_acc = sm + s.prof_acc;
+    prof_acc = grows + a.scratch_stride - 32; /* instrumented builds only: the tail of the per-warp global scratch */
     qpos = sm + s.qpos; qvel = sm + s.qvel; act = sm + s.act; ctrl = sm + s.ctrl; actdot = sm + s.actdot;
     xpos = sm + s.xpos; xquat = sm + s.xquat; com = sm + s.com; cinert = sm + s.cinert; cdof = sm + s.cdof;
     cvel = sm + s.cvel; M = sm + s.M; LD = sm + s.LD;  vbuf = sm + s.vbuf; qfrc_act = sm + s.qfrc_act;
@@ -505,7 +507,7 @@ RR_DEV void kinematics(Ctx<NS> &c) {
 #pragma unroll 1
   for (int rd = 0; rd < R; rd++) {
     for (int b = c.lane; b < nb; b += 32) {
-      const int an = RI(body_anc, rd * nb + b);
+      const int an = RR_BODY_ANC(rd * nb + b);
       float ap[3], aq[4], bp[3], bq[4], r[3], q2[4];
 #pragma unroll
       for (int k = 0; k < 3; k++) { ap[k] = p_in[sp_in * an + k]; bp[k] = p_in[sp_in * b + k]; }
@@ -997,7 +999,7 @@ RR_DEV void tree_prefix6(Ctx<NS> &c, float *&in, float *&out) {
 #pragma unroll 1
   for (int rd = 0; rd < m.nround; rd++) {
     for (int b = c.lane; b < nb; b += 32) {
-      const int an = RI(body_anc, rd * nb + b);
+      const int an = RR_BODY_ANC(rd * nb + b);
       const float2 *ia = reinterpret_cast<const float2 *>(in + 6 * an), *ib = reinterpret_cast<const float2 *>(in + 6 * b);
       float2 *ob = reinterpret_cast<float2 *>(out + 6 * b);
 #pragma unroll

@@ -100,7 +100,6 @@ inline void rr_host_model_build(RRHostModel &hm, const int32_t *dir, const int32
   };
 
   /* ---- bodies ---- */
-  cpI(t_body_parentid, RR_FID(body_parentid));
   cpI(t_body_jntadr, RR_FID(body_jntadr));
   cpI(t_body_jntnum, RR_FID(body_jntnum));
   cpF(t_body_ipos, RR_FID(body_ipos));
@@ -141,19 +140,11 @@ inline void rr_host_model_build(RRHostModel &hm, const int32_t *dir, const int32
       for (int c = 0; c < 4; c++) t_body_equat[4 * b + c] = (float)quat[c];
     }
   }
-  /* tree levels by effective depth (level 0 = world) */
+  /* effective depth of the tree (level 0 = world) */
   std::vector<int> depth(nb, 0);
   int maxd = 0;
   for (int b = 1; b < nb; b++) { depth[b] = depth[t_body_eparent[b]] + 1; maxd = std::max(maxd, depth[b]); }
   d.nlevel = maxd + 1;
-  t_level_adr.assign(d.nlevel + 1, 0);
-  for (int lev = 1; lev <= maxd; lev++) {
-    t_level_adr[lev] = (int)t_level_body.size();
-    for (int b = 1; b < nb; b++) if (depth[b] == lev) t_level_body.push_back(b);
-  }
-  t_level_adr[0] = 0;
-  t_level_adr[d.nlevel] = (int)t_level_body.size();
-  if (t_level_body.empty()) t_level_body.push_back(0);
   /* pointer-doubling tables for the tree scans (kinematics, com_vel): the 2^k-th effective ancestor of every body.
    * A free-joint body takes its pose from qpos whatever its parent is, so it hangs off the world here. */
   {
@@ -167,10 +158,12 @@ inline void rr_host_model_build(RRHostModel &hm, const int32_t *dir, const int32
     int R = 0;
     while ((1 << R) < maxd) R++;
     d.nround = R;
-    t_body_anc.assign((size_t)std::max(R, 1) * nb, 0);
-    for (int b = 0; b < nb; b++) t_body_anc[b] = t_body_eparent[b];
+    std::vector<int> anc((size_t)std::max(R, 1) * nb, 0);
+    for (int b = 0; b < nb; b++) anc[b] = t_body_eparent[b];
     for (int k = 1; k < R; k++)
-      for (int b = 0; b < nb; b++) t_body_anc[(size_t)k * nb + b] = t_body_anc[(size_t)(k - 1) * nb + t_body_anc[(size_t)(k - 1) * nb + b]];
+      for (int b = 0; b < nb; b++) anc[(size_t)k * nb + b] = anc[(size_t)(k - 1) * nb + anc[(size_t)(k - 1) * nb + b]];
+    t_body_anc.assign((anc.size() + 3) / 4, 0); /* one byte per entry (nbody <= 160) */
+    for (size_t e = 0; e < anc.size(); e++) t_body_anc[e >> 2] |= (int32_t)((uint32_t)anc[e] << (8 * (e & 3)));
   }
 
   /* ---- joints ---- */
@@ -376,7 +369,7 @@ inline void rr_host_model_build(RRHostModel &hm, const int32_t *dir, const int32
   int o = 0;
   auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };
   s.qpos = take(nq); s.qvel = take(nv); s.act = take(d.na); s.ctrl = take(nu); s.actdot = take(d.na);
-  s.com = take(3 * d.nroot); s.vbuf = take(nv);  s.xq1 = take(4); s.prof_acc = take(32);
+  s.com = take(3 * d.nroot); s.vbuf = take(nv);  s.xq1 = take(4);
   s.M = take(nM); s.LD = take(std::max(nM, 8 * nb)); /* LD doubles as the second buffer of the tree scans (8 floats per body) */
   s.xpos = take(3 * nb); s.xquat = take(4 * nb); s.cdof = take(6 * nv);
   const int c0 = o;
