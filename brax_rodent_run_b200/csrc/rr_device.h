@@ -63,6 +63,7 @@ struct RRModelDev {
    * constant-bank load -- the solve loops index these once per column without touching the LSU.  Byte offsets (x 4) so that
    * a coefficient address is one add: krow4[i] = 4 rowadr[i], kdep4[i] = 4 depth[i].  Zero beyond nv. */
   int32_t krow4[160], kdep4[160];
+  float kdtd[160];   /* timestep x dof_damping: the diagonal term of the Euler matrix M + dt diag(damping) (factor2) */
   uint8_t kpar[160]; /* body_parentid by value: the leaf-to-root accumulations read it from the constant bank (no LSU round trip in their serial chain) */
   const int32_t *ibuf;
   const float *fbuf;

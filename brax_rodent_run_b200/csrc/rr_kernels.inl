@@ -710,12 +710,12 @@ RR_DEV void factor2(Ctx<NS> &c, float dt) {
       float acc[4][2];
 #pragma unroll
       for (int r = 0; r < 4; r++) {
-        const int kr = k - r < 0 ? 0 : k - r;
-        adr_r[r] = m.krow4[kr] >> 2;
+        /* rows are stored back to back and row k - r has mk - r + 1 entries: rowadr[k - r] = adr - r (mk + 1) + r (r + 1) / 2 */
+        adr_r[r] = adr - r * (mk + 1) + (r * (r + 1)) / 2;
         const bool mine = r < T && g == 0 && s0 <= mk - r;
-        const float v = mine ? L2[adr_r[r] + (mine ? s0 : 0)] : 0.f;
+        const float v = mine ? L2[adr_r[r] + s0] : 0.f;
         acc[r][0] = v;
-        acc[r][1] = v + ((mine && s0 == mk - r) ? dt * RF(dof_damping, kr) : 0.f);
+        acc[r][1] = v; /* dt damping joins the diagonal when the row is finished (one uniform add) */
       }
       for (int jj = c.lane; jj < nd; jj += 32) {
         const int pj = RI(dof_pack, k + 1 + jj), rj = pj & 0xffff, dj = (pj >> 16) & 255;
@@ -737,7 +737,7 @@ RR_DEV void factor2(Ctx<NS> &c, float dt) {
         for (int jj = g; jj < nd; jj += G) {
           const float4 wa = stA[jj], wb = stB[jj];
           const int rj = stR[jj];
-          const float l1 = on ? LD[rj + so] : 0.f, l2 = on ? L2[rj + so] : 0.f;
+          const float l1 = LD[rj + so], l2 = L2[rj + so]; /* lanes beyond the row width accumulate values nobody reads */
           acc[0][0] -= wa.x * l1; acc[0][1] -= wa.y * l2; acc[1][0] -= wa.z * l1; acc[1][1] -= wa.w * l2;
           acc[2][0] -= wb.x * l1; acc[2][1] -= wb.y * l2; acc[3][0] -= wb.z * l1; acc[3][1] -= wb.w * l2;
         }
@@ -746,7 +746,7 @@ RR_DEV void factor2(Ctx<NS> &c, float dt) {
         for (int jj = g; jj < nd; jj += G) {
           const float4 wa = stA[jj];
           const int rj = stR[jj];
-          const float l1 = on ? LD[rj + so] : 0.f, l2 = on ? L2[rj + so] : 0.f;
+          const float l1 = LD[rj + so], l2 = L2[rj + so];
           acc[0][0] -= wa.x * l1; acc[0][1] -= wa.y * l2; acc[1][0] -= wa.z * l1; acc[1][1] -= wa.w * l2;
         }
       }
@@ -764,7 +764,7 @@ RR_DEV void factor2(Ctx<NS> &c, float dt) {
       for (int r = 0; r < 4; r++) {
         if (r < T) {
           const int dg = mk - r; /* diagonal position of row k - r */
-          const float d1 = __shfl_sync(RR_FULL, acc[r][0], dg), d2 = __shfl_sync(RR_FULL, acc[r][1], dg);
+          const float d1 = __shfl_sync(RR_FULL, acc[r][0], dg), d2 = __shfl_sync(RR_FULL, acc[r][1], dg) + m.kdtd[k - r];
           const float l1 = acc[r][0] * RR_RCP(d1), l2 = acc[r][1] * RR_RCP(d2);
 #pragma unroll
           for (int q = r + 1; q < 4; q++) {
@@ -773,8 +773,10 @@ RR_DEV void factor2(Ctx<NS> &c, float dt) {
               acc[q][0] -= u1 * l1; acc[q][1] -= u2 * l2;
             }
           }
-          if (g == 0 && s0 < dg) { LD[adr_r[r] + s0] = l1; L2[adr_r[r] + s0] = l2; }
-          if (c.lane == 0) { LD[adr_r[r] + dg] = d1; L2[adr_r[r] + dg] = d2; }
+          if (g == 0 && s0 <= dg) { /* the lane of the diagonal stores D (inverted at the end of the sweep), the others L */
+            LD[adr_r[r] + s0] = s0 == dg ? d1 : l1;
+            L2[adr_r[r] + s0] = s0 == dg ? d2 : l2;
+          }
         }
       }
       __syncwarp();

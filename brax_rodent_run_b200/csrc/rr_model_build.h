@@ -208,6 +208,7 @@ inline void rr_host_model_build(RRHostModel &hm, const int32_t *dir, const int32
   for (int i = 0; i < nv; i++) t_dof_pack[i] = t_dof_rowadr[i] | (t_dof_depth[i] << 16) | (t_dof_ndesc[i] << 24);
   for (int i = 0; i < 160; i++) { d.krow4[i] = i < nv ? 4 * t_dof_rowadr[i] : 0; d.kdep4[i] = i < nv ? 4 * t_dof_depth[i] : 0; }
   for (int b = 0; b < 160; b++) d.kpar[b] = (uint8_t)(b < nb ? parent[b] : 0);
+  for (int i = 0; i < 160; i++) d.kdtd[i] = i < nv ? d.timestep * t_dof_damping[i] : 0.f;
   /* per dof and block of 32 columns: which columns are descendants / ancestors of the dof (the solves' predicates) */
   {
     const int nb32 = (nv + 31) / 32;
