@@ -1302,7 +1302,7 @@ RR_DEV void mul_j(Ctx<NS> &c, float *out) {
   for (int r = c.lane; r < c.nla; r += 32) {
     int id = c.row_id[r];
     float sg = (id & RR_SIGN_BIT) ? -1.f : 1.f;
-    out[r] = sg * c.vbuf[RI(limit_dofadr, id & 0xffff)];
+    out[r] = sg * c.vbuf[(id >> 16) & 255];
   }
   /* V_b for every contact body: item = (body slot, component) */
   for (int it = c.lane; it < 6 * m.ncb; it += 32) {
@@ -1319,8 +1319,8 @@ RR_DEV void mul_j(Ctx<NS> &c, float *out) {
   }
   __syncwarp();
   for (int k = c.lane; k < c.nca; k += 32) {
-    const int cc = c.cact[k];
-    const float *ab = c.cab + 12 * cc, *V = c.cbv + 6 * RI(pair_cb, RI(con_pair, cc));
+    const int ck = c.cact[k], cc = ck & 255; /* cact: contact | pair << 8 | contact body << 20 (packed by make_constraint) */
+    const float *ab = c.cab + 12 * cc, *V = c.cbv + 6 * (ck >> 20);
     const float off[3] = {ab[9], ab[10], ab[11]}, va[3] = {V[0], V[1], V[2]};
     float u[3];
     cross3(u, va, off);
@@ -1332,7 +1332,7 @@ RR_DEV void mul_j(Ctx<NS> &c, float *out) {
   __syncwarp();
   for (int r = c.lane; r < 4 * c.nca; r += 32) {
     int k = r >> 2, q = r & 3;
-    float mu = RF(pair_mu, RI(con_pair, c.cact[k]));
+    float mu = RF(pair_mu, (c.cact[k] >> 8) & 4095);
     float f = (q & 1) ? -mu : mu;
     out[c.nla + r] = c.cscr[6 * k] + c.cscr[6 * k + 1 + (q >> 1)] * f;
   }
@@ -1349,12 +1349,12 @@ RR_DEV void mul_jt(Ctx<NS> &c, const float *frc, float (&qfc)[NS]) {
   for (int r = c.lane; r < c.nla; r += 32) {
     int id = c.row_id[r];
     float sg = (id & RR_SIGN_BIT) ? -1.f : 1.f;
-    c.vbuf[RI(limit_dofadr, id & 0xffff)] = sg * frc[r];
+    c.vbuf[(id >> 16) & 255] = sg * frc[r];
   }
   for (int k = c.lane; k < c.nca; k += 32) {
     const float *f = frc + c.nla + 4 * k;
-    const int cc = c.cact[k];
-    const float mu = RF(pair_mu, RI(con_pair, cc));
+    const int ck = c.cact[k], cc = ck & 255;
+    const float mu = RF(pair_mu, (ck >> 8) & 4095);
     const float g0 = f[0] + f[1] + f[2] + f[3], g1 = mu * f[0] - mu * f[1], g2 = mu * f[2] - mu * f[3];
     const float *ab = c.cab + 12 * cc;
     float w[3], t[3];
@@ -1427,7 +1427,7 @@ RR_DEV void make_constraint(Ctx<NS> &c) {
     unsigned mask = __ballot_sync(RR_FULL, active);
     if (cc < m.ncon) {
       int k = nca + __popc(mask & lt);
-      if (active) c.cact[k] = cc;
+      if (active) { const int pp = RI(con_pair, cc); c.cact[k] = cc | (pp << 8) | (RI(pair_cb, pp) << 20); }
       c.ckidx[cc] = active ? k : -1;
     }
     nca += __popc(mask);
@@ -1459,7 +1459,7 @@ RR_DEV void make_constraint(Ctx<NS> &c) {
       for (int q = 0; q < 5; q++) si[q] = RF(limit_solimp, 5 * l + q);
       kbi(m.timestep, sr, si, pos, k, b, imp);
       float R = fmaxf(RF(limit_invweight, l) * (1.f - imp) * RR_RCP(imp), RR_MINVAL);
-      c.row_id[r] = l | (dlo < dhi ? 0 : RR_SIGN_BIT);
+      c.row_id[r] = l | (RI(limit_dofadr, l) << 16) | (dlo < dhi ? 0 : RR_SIGN_BIT); /* row | dof << 16 | sign */
       c.row_D[r] = RR_RCP(R);
       c.row_aref[r] = k * imp * pos; /* temp: completed below */
       c.row_Jaref[r] = b;            /* temp */
@@ -1468,7 +1468,7 @@ RR_DEV void make_constraint(Ctx<NS> &c) {
   }
   /* active contacts: row parameters (the frame and the point stay as collision() left them) */
   for (int k = c.lane; k < nca; k += 32) {
-    int cc = c.cact[k];
+    int cc = c.cact[k] & 255;
     int p = RI(con_pair, cc);
     float pos = c.con_dist[cc] - RF(pair_margin, p);
     float sr[2] = {RF(pair_solref, 2 * p), RF(pair_solref, 2 * p + 1)}, si[5], kk, b, imp;
@@ -1500,7 +1500,7 @@ RR_DEV void make_constraint(Ctx<NS> &c) {
       dD[l] = c.row_D[r];
     }
     for (int k = 0; k < nca; k++) {
-      int cc = c.cact[k];
+      int cc = c.cact[k] & 255;
       int p = RI(con_pair, cc);
       int ld = RI(pair_lastdof, p);
       int len = RI(dof_depth, ld) + 1, adr = RI(dof_rowadr, ld);

@@ -313,6 +313,7 @@ inline void rr_host_model_build(RRHostModel &hm, const int32_t *dir, const int32
   if (t_cb_lastdof.empty()) t_cb_lastdof.push_back(0);
   /* per dof: bit kb set when the chain of contact body kb contains the dof (mul_jt gathers only over these) */
   if (d.ncb > 64) throw std::runtime_error("NotImplemented: more than 64 bodies with collision geoms");
+  if (nc > 255 || np > 4095) throw std::runtime_error("NotImplemented: more than 255 contacts / 4095 collision pairs");
   t_dof_cbmask.assign(2 * std::max(nv, 1), 0);
   for (int kb = 0; kb < d.ncb; kb++)
     for (int dd = t_cb_lastdof[kb]; dd >= 0; dd = dofparent[dd]) t_dof_cbmask[2 * dd + (kb >> 5)] |= (int32_t)(1u << (kb & 31));
