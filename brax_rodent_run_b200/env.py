@@ -229,6 +229,7 @@ class Rodent:
         xml_path: Optional[str] = None,
         kinematics_outputs: bool = True,
         balance: bool = False,
+        reuse_buffers: bool = False,
         _lib_path: Optional[str] = None,
         **kwargs,
     ):
@@ -246,6 +247,12 @@ class Rodent:
         self.backend = "b200"
         self.num_envs = int(num_envs)
         self._kin = bool(kinematics_outputs)
+        # reuse_buffers: step() cycles through THREE preallocated output sets instead of allocating ten tensors per call.  A
+        # State stays valid until the third step() after the one that produced it (enough for `s = env.step(s, a)` loops
+        # and for holding on to the previous state); anything kept longer must be cloned.  Off by default: brax States are
+        # immutable, and that is what the default gives.
+        self._reuse = bool(reuse_buffers)
+        self._ring, self._ring_pos = [], 0
 
         dir_, idata, fdata = model_blob.pack(flat)
         self._blob = (np.ascontiguousarray(dir_, np.int32), np.ascontiguousarray(idata, np.int32),
@@ -394,7 +401,17 @@ class Rodent:
     def _empty(self, *shape, dtype=torch.float32):
         return torch.empty(shape, dtype=dtype, device=self.device)
 
-    def _out_buffers(self) -> Tuple[_lib.RRBuffers, Dict[str, torch.Tensor]]:
+    def _out_buffers(self, ring: bool = False) -> Tuple[_lib.RRBuffers, Dict[str, torch.Tensor]]:
+        if ring and self._reuse:
+            if len(self._ring) < 3:
+                self._ring.append(self._out_buffers())
+                return self._ring[-1]
+            self._ring_pos = (self._ring_pos + 1) % 3
+            buf, t = self._ring[self._ring_pos]
+            fresh = _lib.RRBuffers()
+            for k, v in t.items():
+                setattr(fresh, k, v.data_ptr())
+            return fresh, t
         B, d = self.num_envs, self.dims
         t = dict(qpos=self._empty(B, d.nq), qvel=self._empty(B, d.nv), act=self._empty(B, d.na),
                  qacc_warmstart=self._empty(B, d.nv), time=self._empty(B), cur_frame=self._empty(B, dtype=torch.int32),
@@ -475,7 +492,7 @@ class Rodent:
     def step(self, state: State, action: torch.Tensor) -> State:
         B = self.num_envs
         action = action.to(self.device, torch.float32).reshape(B, self.sys.nu).contiguous()
-        buf, t = self._out_buffers()
+        buf, t = self._out_buffers(ring=True)
         ps = state.pipeline_state
         buf.in_qpos, buf.in_qvel, buf.in_act = ps.qpos.data_ptr(), ps.qvel.data_ptr(), ps.act.data_ptr()
         buf.in_qacc_warmstart, buf.in_time = ps.qacc_warmstart.data_ptr(), ps.time.data_ptr()

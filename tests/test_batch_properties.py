@@ -100,3 +100,22 @@ def test_emulator_lane_order_independence(emu_lib, make_env, monkeypatch):
     for o in outs[1:]:
         for a, b in zip(outs[0], o):
             assert np.array_equal(a, b)
+
+
+def test_reuse_buffers_matches_fresh_allocation(make_env):
+    """Rodent(reuse_buffers=True) cycles three preallocated output sets; a `s = env.step(s, a)` loop gives bit-identical states."""
+    m = load_asset("rodent_0")
+    rng = np.random.default_rng(5)
+    acts = rng.uniform(-1, 1, (5, 2, m.nu)).astype(np.float32)
+    outs = []
+    for reuse in (False, True):
+        env = make_env("emu", synthetic_track(), num_envs=2, model=m, iterations=2, ls_iterations=2, n_frames=1,
+                       reuse_buffers=reuse).wrap_for_training(3)
+        s = env.reset(4)
+        prev = None
+        for t in range(5):
+            prev, s = s, env.step(s, torch.tensor(acts[t]))
+            assert prev.obs.data_ptr() != s.obs.data_ptr()  # the previous state is still intact
+        outs.append((s.obs.numpy().copy(), s.pipeline_state.qpos.numpy().copy(), s.info["steps"].numpy().copy()))
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)
