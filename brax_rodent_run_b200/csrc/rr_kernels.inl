@@ -1126,6 +1126,69 @@ RR_DEV void com_vel_and_rne(Ctx<NS> &c, float (&qfrc_bias)[NS]) {
   }
 }
 
+/* y = M v from the bodies' own inertias instead of the assembled matrix: M = sum_b J_b' I_b J_b (+ armature), so
+ *   A_b = prefix sum over the chain of b of cdof v   (tree_prefix6, as com_vel),   F_b = I_b A_b  (cinert, inert_mul),
+ *   y_d = cdof_d . (sum of F over the subtree of body(d)) + armature_d v_d          (leaf-to-root accumulation, as rne).
+ * Same bilinear form as crb_and_mass_matrix builds, O(nbody) work on all lanes instead of a row + column walk per dof in
+ * which the root dofs alone visit 72 descendants (mul_m: 1.5 k instructions per call, 6 busy lanes for most of them).
+ * Needs cinert and cdof of the current pose and uses cvel / cacc / LD as scratch: only valid between smooth_forces and the
+ * factorisation (the M qacc_warmstart product of the solver's warm start). */
+template <int NS>
+RR_DEV void mul_m_tree(Ctx<NS> &c, float (&y)[NS], const float (&v)[NS]) {
+  const RRModelDev &m = c.m;
+  const int nb = m.nbody;
+  const bool odd = m.nround & 1;
+  __syncwarp();
+  vstore<NS>(c, v, c.vbuf);
+  __syncwarp();
+  float *in = odd ? c.cvel : c.LD, *out = odd ? c.LD : c.cvel; /* nround swaps end in LD */
+  for (int b = c.lane; b < nb; b += 32) {
+    float av[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const int jadr = RI(body_jntadr, b), jnum = RI(body_jntnum, b);
+    for (int j = jadr; j < jadr + jnum; j++) {
+      const int d0 = RI(jnt_dofadr, j), nd = RI(jnt_type, j) == RR_JNT_FREE ? 6 : 1;
+      for (int d = 0; d < nd; d++) {
+        const float qv = c.vbuf[d0 + d];
+#pragma unroll
+        for (int k = 0; k < 6; k++) av[k] += c.cdof[6 * (d0 + d) + k] * qv;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 6; k++) in[6 * b + k] = av[k];
+  }
+  __syncwarp();
+  tree_prefix6<NS>(c, in, out); /* `in` = LD now holds A_b */
+  for (int b = c.lane; b < nb; b += 32) {
+    float ci[10], a6[6], f[6];
+#pragma unroll
+    for (int k = 0; k < 10; k++) ci[k] = c.cinert[10 * b + k];
+#pragma unroll
+    for (int k = 0; k < 6; k++) a6[k] = in[6 * b + k];
+    inert_mul(f, ci, a6);
+#pragma unroll
+    for (int k = 0; k < 6; k++) c.cfrc[6 * b + k] = f[k];
+  }
+  __syncwarp();
+#pragma unroll 4
+  for (int b = nb - 1; b > 0; b--) { /* lane q owns component q */
+    const int p = m.kpar[b];
+    if (c.lane < 6 && p > 0) c.cfrc[6 * p + c.lane] += c.cfrc[6 * b + c.lane];
+  }
+  __syncwarp();
+  RR_FOR_S {
+    const int i = c.lane + 32 * s;
+    float acc = 0.f;
+    if (i < m.nv) {
+      const int b = RI(dof_bodyid, i);
+      acc = RF(dof_armature, i) * v[s];
+#pragma unroll
+      for (int k = 0; k < 6; k++) acc += c.cdof[6 * i + k] * c.cfrc[6 * b + k];
+    }
+    y[s] = acc;
+  }
+  __syncwarp();
+}
+
 /* passive + actuation -> qfrc_smooth (qacc_smooth = M^-1 qfrc_smooth is solved by the caller) */
 template <int NS>
 RR_DEV void smooth_forces(Ctx<NS> &c, const float (&qfrc_bias)[NS]) {
@@ -1896,7 +1959,7 @@ RR_DEV void substep(Ctx<NS> &c, bool integrate, float &time, int sub) {
   }
   if (c.last_substep) forward_outputs<NS>(c);
   dbg_copy<NS>(c, RR_DBG_M, c.M, m.nM);
-  mul_m<NS>(c, c.ma_warm, c.warm); /* the only product with M the solver needs (see ctx_init) */
+  mul_m_tree<NS>(c, c.ma_warm, c.warm); /* the only product with M the solver needs (see ctx_init) */
   prof<NS>(c, RR_PROF_MULM);
   RR_CTA_SYNC_IF(RR_SYNC_LEVEL >= 2 && RR_SYNC_FACTOR);
   __syncwarp();
