@@ -378,7 +378,7 @@ def run_b200(args):
 def measure_extra(args, dev, world, rank):
     """The other half of BASELINE.json's metric and configs[4], measured after the timed region of the contract line and
     appended to the same JSON line: PPO train SPS (2048 envs / GPU, README configuration, NCCL gradient all-reduce when
-    world > 1) and rodent_pair env-steps/s (4096 envs / GPU).  Bounded: 1 + 2 training steps, 3 + 10 env steps."""
+    world > 1) and rodent_pair env-steps/s (4096 envs / GPU).  Bounded: 1 + 3 training steps, 3 + 10 env steps."""
     import torch
     import torch.distributed as dist
     from brax_rodent_run_b200 import ppo
@@ -395,14 +395,14 @@ def measure_extra(args, dev, world, rank):
         if world > 1:
             dist.barrier()
         e0, t0 = agent.env_steps, time.perf_counter()
-        for _ in range(2):
+        for _ in range(3):
             state, _ = agent.training_step(state)
         torch.cuda.synchronize(dev)
         dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         out["ppo_train_sps"] = {"value": (agent.env_steps - e0) / float(dt.item()), "unit": "env-steps/s", "envs_per_gpu": 2048,
-                                "n_gpus": world, "training_steps": 2,
+                                "n_gpus": world, "training_steps": 3,
                                 "config": "readme.md:17-31: unroll 10, batch 512 x 64 minibatches, 8 epochs, CG 8/8, normalised obs"}
         del agent, env, state
     except Exception as ex:  # the contract line must survive a failure of an extra
