@@ -52,6 +52,14 @@ class RRPpoLossArgs(ctypes.Structure):
                 [(n, vp) for n in ("scratch", "adv_partial", "loss_partial", "grad_logits", "grad_baseline")])
 
 
+class RRTcProblem(ctypes.Structure):
+    """rr_tc_problem (include/rr_b200.h): one GEMM of a grouped tensor-core launch."""
+    _fields_ = ([(n, vp) for n in ("a", "b", "d", "bias", "aux_in", "aux_out", "ones_out")] +
+                [(n, ctypes.c_int32) for n in ("m", "n", "k", "lda", "ldb", "ldd", "ldaux", "a_mn", "b_mn", "epi", "b_ones",
+                                               "bn", "tile_start", "tiles_n")] +
+                [("reserved", ctypes.c_int32 * 4)])
+
+
 _libs = {}
 
 
@@ -93,6 +101,10 @@ def load(path: Optional[str] = None):
     L.rr_measure_fp32_peak.argtypes = [ctypes.POINTER(ctypes.c_double), vp]
     L.rr_measure_fp32_peak.restype = ctypes.c_int
     L.rr_launch_count.restype = ctypes.c_longlong
+    L.rr_tc_plan.argtypes = [ctypes.POINTER(RRTcProblem), ctypes.c_int32, c_i, c_i]
+    L.rr_tc_plan.restype = ctypes.c_int
+    L.rr_tc_launch.argtypes = [vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, vp]
+    L.rr_tc_launch.restype = ctypes.c_int
     for name in ("rr_model_create", "rr_model_set_solver", "rr_model_dims", "rr_env_create", "rr_env_set_task",
                  "rr_env_set_wrappers", "rr_env_geometry", "rr_env_init", "rr_env_step", "rr_env_step_host", "rr_gae", "rr_debug_field",
                  "rr_env_set_debug", "rr_env_set_profile", "rr_ppo_loss", "rr_ppo_loss_blocks"):

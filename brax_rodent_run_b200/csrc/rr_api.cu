@@ -277,4 +277,24 @@ static int rrb_launch_ppo_loss(const RRPpoLossArgs &a, void *stream) {
   return rrb_check(cudaGetLastError(), "rr_ppo_loss launch");
 }
 
+/* grouped TF32 GEMM of the learner on the tensor cores (tcgen05) */
+#define RR_TC_HD __host__ __device__ static inline
+#include "rr_tc_gemm.h"
+#define RR_TC_BN_MAX 128
+static int rrb_tc_smem_max() { return RR_TC_STAGES * (RR_TC_BM + RR_TC_BN_MAX) * RR_TC_BK * 4; }
+static int rrb_tc_launch(const rr_tc_problem *dev_probs, int count, int total_tiles, int smem_bytes, void *stream) {
+  static std::atomic<bool> configured[64];
+  int dev = 0;
+  if (rrb_check(cudaGetDevice(&dev), "cudaGetDevice")) return 1;
+  dev &= 63;
+  if (!configured[dev].load(std::memory_order_acquire)) {
+    if (rrb_check(cudaFuncSetAttribute(rr_tc::gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, rrb_tc_smem_max()),
+                  "rr_tc gemm_kernel attribute"))
+      return 1;
+    configured[dev].store(true, std::memory_order_release);
+  }
+  rr_tc::gemm_kernel<<<total_tiles, RR_TC_THREADS, smem_bytes, (cudaStream_t)stream>>>(dev_probs, count);
+  return rrb_check(cudaGetLastError(), "rr_tc gemm_kernel launch");
+}
+
 #include "rr_api_impl.inl"

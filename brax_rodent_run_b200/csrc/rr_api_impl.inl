@@ -357,6 +357,42 @@ extern "C" int rr_ppo_loss(const rr_ppo_loss_args *u, void *stream) {
   return RR_OK;
 }
 
+/* ---- grouped tensor-core GEMM of the learner ------------------------------------------------------------------ */
+extern "C" int rr_tc_plan(rr_tc_problem *pr, int32_t count, int32_t *total_tiles, int32_t *smem_bytes) {
+  if (!pr || count < 1 || count > 64 || !total_tiles || !smem_bytes) return rr_fail(RR_EINVAL, "rr_tc_plan: bad argument");
+  int tiles = 0, bn_max = 16;
+  for (int i = 0; i < count; i++) {
+    rr_tc_problem &p = pr[i];
+    if (p.m < 1 || p.n < 1 || p.k < 1 || !p.a || !p.b || !p.d) return rr_fail(RR_EINVAL, "rr_tc_plan: empty problem or null matrix");
+    if (p.epi < 0 || p.epi > 2 || (p.epi == 2 && !p.aux_in)) return rr_fail(RR_EINVAL, "rr_tc_plan: bad epilogue");
+    if (p.b_ones && (!p.b_mn || !p.ones_out)) return rr_fail(RR_EINVAL, "rr_tc_plan: b_ones needs an MN-major B and ones_out");
+    if (p.lda < (p.a_mn ? p.m : p.k) || p.ldb < (p.b_mn ? p.n : p.k) || p.ldd < p.n ||
+        ((p.epi == 2 || (p.epi == 1 && p.aux_out)) && p.ldaux < p.n))
+      return rr_fail(RR_EINVAL, "rr_tc_plan: leading dimension smaller than the row length");
+    const int n_ext = p.n + (p.b_ones ? 1 : 0), tiles_m = (p.m + 127) / 128;
+    /* narrow tiles (64) keep more SMs busy when there are few row tiles; 128 otherwise */
+    int cap = (tiles_m * ((n_ext + 63) / 64) <= 2 * 148) ? 64 : 128;
+    int bn = (n_ext + 15) / 16 * 16;
+    if (bn > cap) bn = cap;
+    p.bn = bn;
+    p.tiles_n = (n_ext + bn - 1) / bn;
+    p.tile_start = tiles;
+    tiles += tiles_m * p.tiles_n;
+    if (bn > bn_max) bn_max = bn;
+  }
+  *total_tiles = tiles;
+  *smem_bytes = 4 * (128 * 128 + (bn_max + 31) / 32 * 4096); /* RR_TC_STAGES x (A tile + B tile) of one 32-wide k-block */
+  if (*smem_bytes > rrb_tc_smem_max()) return rr_fail(RR_EINVAL, "rr_tc_plan: tile does not fit shared memory");
+  return RR_OK;
+}
+
+extern "C" int rr_tc_launch(const rr_tc_problem *dev_problems, int32_t count, int32_t total_tiles, int32_t smem_bytes, void *stream) {
+  if (!dev_problems || count < 1 || total_tiles < 1 || smem_bytes < 1) return rr_fail(RR_EINVAL, "rr_tc_launch: bad argument");
+  if (rrb_tc_launch(dev_problems, count, total_tiles, smem_bytes, stream)) return rr_fail(RR_ECUDA, rrb_error());
+  g_rr_launches += 1;
+  return RR_OK;
+}
+
 extern "C" int rr_measure_fp32_peak(double *tflops, void *stream) {
   if (!tflops) return rr_fail(RR_EINVAL, "rr_measure_fp32_peak: null argument");
   if (rrb_fp32_peak(tflops, stream)) return rr_fail(RR_ECUDA, rrb_error());

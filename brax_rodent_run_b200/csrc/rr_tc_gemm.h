@@ -1,0 +1,311 @@
+/* rr_tc_gemm.h -- grouped TF32 GEMM on the Blackwell tensor cores (tcgen05.mma kind::tf32, accumulator in tensor memory) with
+ * the learner's epilogues fused (bias, SiLU, SiLU-derivative scaling, bias-gradient column).  See rr_tc_problem in
+ * include/rr_b200.h for the semantics; the host-side reference of the same semantics is rr_tc_reference() below (used by the
+ * emulator backend under tests/emu so that the Python learner's problem lists can be checked on the CPU).
+ *
+ * One CTA (128 threads) owns one 128 x bn output tile:
+ *   - all four warps stream the k-blocks (32 wide) of A and B with cp.async, 16 bytes at a time, straight into the UMMA
+ *     canonical shared-memory layouts:
+ *         K-major operand, no swizzle: core matrix = 8 rows x 16 bytes, contiguous 128 B; core (row / 8, k / 4) at
+ *             (row / 8) * 1024 + (k / 4) * 128                                                     [SBO 1024, LBO 128]
+ *         MN-major operand: the only layout the hardware takes for 32-bit MN-major operands is the 128-byte swizzle with
+ *             32-byte atomicity (UMMA layout type 1): atom = 4 k-lines x 128 bytes (32 rows); 32-byte unit u of line k % 4
+ *             sits at unit u ^ (k % 4); atom (row / 32, k / 4) at (row / 32) * 4096 + (k / 4) * 512   [LBO 4096, SBO 512]
+ *     so row-major X, W (K-major for X W') and the same arrays read "transposed" (MN-major, for dY W and dY' X) need no copy;
+ *     ragged edges are zero-filled in shared memory, a virtual row of ones gives the bias gradient;
+ *   - RR_TC_STAGES-deep ring: cp.async.wait_group -> fence.proxy.async -> __syncthreads -> thread 0 issues the four
+ *     tcgen05.mma (K = 8 each) of the stage and tcgen05.commit's to the stage's mbarrier, which the loaders wait on before
+ *     they overwrite the stage;
+ *   - epilogue: each warp reads its 32 TMEM lanes (= rows) with tcgen05.ld 32x32b.x16, applies the epilogue and stores rows.
+ */
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/rr_b200.h"
+
+#define RR_TC_BM 128
+#define RR_TC_BK 32
+#define RR_TC_STAGES 4
+#define RR_TC_THREADS 128
+
+RR_TC_HD float rr_tc_sigmoid(float z) { return 1.f / (1.f + expf(-z)); }
+RR_TC_HD float rr_tc_epilogue(const rr_tc_problem &p, int row, int col, float acc) {
+  float v = acc + (p.bias ? p.bias[col] : 0.f);
+  if (p.epi == 1) {
+    if (p.aux_out) p.aux_out[(size_t)row * p.ldaux + col] = v;
+    v = v * rr_tc_sigmoid(v);
+  } else if (p.epi == 2) {
+    const float z = p.aux_in[(size_t)row * p.ldaux + col], s = rr_tc_sigmoid(z);
+    v *= s * (1.f + z * (1.f - s));
+  }
+  return v;
+}
+
+/* plain loops with the same semantics (fp32 products): emulator backend and documentation of the contract */
+static inline void rr_tc_reference(const rr_tc_problem &p) {
+  for (int r = 0; r < p.m; r++) {
+    for (int c = 0; c < p.n + (p.b_ones ? 1 : 0); c++) {
+      float acc = 0.f;
+      for (int kk = 0; kk < p.k; kk++) {
+        const float av = p.a_mn ? p.a[(size_t)kk * p.lda + r] : p.a[(size_t)r * p.lda + kk];
+        const float bv = c == p.n ? 1.f : (p.b_mn ? p.b[(size_t)kk * p.ldb + c] : p.b[(size_t)c * p.ldb + kk]);
+        acc += av * bv;
+      }
+      if (c == p.n) p.ones_out[r] = acc;
+      else p.d[(size_t)r * p.ldd + c] = rr_tc_epilogue(p, r, c, acc);
+    }
+  }
+}
+
+#ifdef __CUDACC__
+namespace rr_tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+/* bounded: a broken pipeline traps instead of hanging the GPU */
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  for (uint32_t spin = 0;; spin++) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+    if (spin > (1u << 22)) __trap();
+  }
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void st_shared_f32(uint32_t dst, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(dst), "f"(v) : "memory");
+}
+__device__ __forceinline__ void st_shared_zero16(uint32_t dst) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "f"(0.f) : "memory");
+}
+
+/* shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address, leading / stride byte offsets in 16-byte units,
+ * version 1 (Blackwell), layout type in bits 61-63 (0 no swizzle, 1 = 128-byte swizzle with 32-byte atomicity) */
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
+  return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) |
+         (1ull << 46) | ((uint64_t)layout_type << 61);
+}
+
+struct Operand {
+  const float *base;
+  int rows, ld, mn, row0, tile_rows, fast, ones_row; /* ones_row: global row index that reads as 1 (or -1) */
+};
+
+/* one k-block of one operand tile into shared memory; every thread handles chunks tid, tid + 128, ... (a chunk = one 16-byte
+ * line of a core matrix) */
+__device__ __forceinline__ void load_tile(const Operand &o, uint32_t sbase, int kb, int K, int tid) {
+  const int nchunk = o.tile_rows * (RR_TC_BK / 4);
+  const int kbase = kb * RR_TC_BK;
+  if (!o.mn) {
+    for (int c = tid; c < nchunk; c += RR_TC_THREADS) {
+      const int l = c & 7, kc = (c >> 3) & 7, cr = c >> 6;
+      const int row = o.row0 + cr * 8 + l, k0 = kbase + kc * 4;
+      const uint32_t dst = sbase + cr * 1024 + kc * 128 + l * 16;
+      int cnt = K - k0;
+      cnt = row < o.rows ? (cnt > 4 ? 4 : cnt) : 0;
+      const float *src = o.base + (size_t)row * o.ld + k0;
+      if (cnt == 4 && o.fast) cp_async16(dst, src);
+      else if (cnt <= 0) st_shared_zero16(dst);
+      else {
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          if (e < cnt) cp_async4(dst + 4 * e, src + e);
+          else st_shared_f32(dst + 4 * e, 0.f);
+        }
+      }
+    }
+  } else {
+    /* a warp's 32 consecutive chunks = one 512-byte swizzle atom: 4 k-lines of 128 contiguous bytes (32 rows) each */
+    const int nchunk_mn = ((o.tile_rows + 31) >> 5) * 32 * (RR_TC_BK / 4);
+    for (int c = tid; c < nchunk_mn; c += RR_TC_THREADS) {
+      const int j = c & 7, kr = (c >> 3) & 3, rest = c >> 5, kq = rest & 7, mb = rest >> 3;
+      const int k = kbase + kq * 4 + kr, r0 = o.row0 + mb * 32 + j * 4;
+      const uint32_t dst = sbase + mb * 4096 + kq * 512 + kr * 128 + ((((j >> 1) ^ kr) << 5) | ((j & 1) << 4));
+      int cnt = o.rows - r0;
+      cnt = k < K ? (cnt > 4 ? 4 : cnt) : 0;
+      const float *src = o.base + (size_t)k * o.ld + r0;
+      const int one = (k < K && o.ones_row >= r0 && o.ones_row < r0 + 4) ? o.ones_row - r0 : -1;
+      if (cnt == 4 && o.fast) cp_async16(dst, src);
+      else if (cnt <= 0 && one < 0) st_shared_zero16(dst);
+      else {
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          if (e < cnt) cp_async4(dst + 4 * e, src + e);
+          else st_shared_f32(dst + 4 * e, e == one ? 1.f : 0.f);
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(RR_TC_THREADS) gemm_kernel(const rr_tc_problem *__restrict__ probs, int nprob) {
+  extern __shared__ __align__(1024) uint8_t tc_smem[];
+  __shared__ __align__(8) uint64_t bars[RR_TC_STAGES];
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  /* which problem, which tile */
+  int pi = 0;
+  for (int i = 1; i < nprob; i++)
+    if ((int)blockIdx.x >= probs[i].tile_start) pi = i;
+  const rr_tc_problem p = probs[pi];
+  const int t = blockIdx.x - p.tile_start, tile_m = t / p.tiles_n, tile_n = t % p.tiles_n;
+  const int BN = p.bn, K = p.k, nkb = (K + RR_TC_BK - 1) / RR_TC_BK;
+  const int n_ext = p.n + (p.b_ones ? 1 : 0);
+
+  Operand oa, ob;
+  oa.base = p.a; oa.rows = p.m; oa.ld = p.lda; oa.mn = p.a_mn; oa.row0 = tile_m * RR_TC_BM; oa.tile_rows = RR_TC_BM;
+  oa.fast = (p.lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.a) & 15) == 0); oa.ones_row = -1;
+  ob.base = p.b; ob.rows = p.n; ob.ld = p.ldb; ob.mn = p.b_mn; ob.row0 = tile_n * BN; ob.tile_rows = BN;
+  ob.fast = (p.ldb % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.b) & 15) == 0); ob.ones_row = p.b_ones ? p.n : -1;
+
+  const uint32_t smem0 = smem_u32(tc_smem);
+  const uint32_t a_bytes = RR_TC_BM * RR_TC_BK * 4, b_bytes = (uint32_t)((BN + 31) >> 5) * 4096, stage_bytes = a_bytes + b_bytes;
+  uint32_t ncols = 32;
+  while ((int)ncols < BN) ncols <<= 1;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+    for (int s = 0; s < RR_TC_STAGES; s++) mbar_init(smem_u32(&bars[s]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_slot;
+
+  /* instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A / B tf32, majors, N >> 3, M >> 4 */
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.a_mn & 1) << 15) | ((uint32_t)(p.b_mn & 1) << 16) |
+                         ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(RR_TC_BM >> 4) << 24);
+  /* per-MMA (K = 8) descriptor geometry */
+  const uint32_t a_lbo = p.a_mn ? 4096 : 128, a_sbo = p.a_mn ? 512 : 1024, a_step = p.a_mn ? 1024 : 256, a_type = p.a_mn ? 1 : 0;
+  const uint32_t b_lbo = p.b_mn ? 4096 : 128, b_sbo = p.b_mn ? 512 : 1024, b_step = p.b_mn ? 1024 : 256, b_type = p.b_mn ? 1 : 0;
+
+  for (int s = 0; s < RR_TC_STAGES - 1; s++) {
+    if (s < nkb) {
+      load_tile(oa, smem0 + s * stage_bytes, s, K, tid);
+      load_tile(ob, smem0 + s * stage_bytes + a_bytes, s, K, tid);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  for (int kb = 0; kb < nkb; kb++) {
+    const int s = kb % RR_TC_STAGES;
+    asm volatile("cp.async.wait_group %0;" ::"n"(RR_TC_STAGES - 2) : "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t sa = smem0 + s * stage_bytes, sb = sa + a_bytes;
+#pragma unroll
+      for (int j = 0; j < RR_TC_BK / 8; j++) {
+        const uint64_t da = make_desc(sa + j * a_step, a_lbo, a_sbo, a_type), db = make_desc(sb + j * b_step, b_lbo, b_sbo, b_type);
+        const uint32_t accumulate = (kb > 0 || j > 0) ? 1u : 0u;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+            : "memory");
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bars[s])) : "memory");
+    }
+    const int nxt = kb + RR_TC_STAGES - 1;
+    if (nxt < nkb) {
+      const int sn = nxt % RR_TC_STAGES; /* == (kb - 1) % STAGES: free once the MMAs of k-block kb - 1 have read it */
+      if (kb >= 1) mbar_wait(smem_u32(&bars[sn]), (uint32_t)(((kb - 1) / RR_TC_STAGES) & 1));
+      load_tile(oa, smem0 + sn * stage_bytes, nxt, K, tid);
+      load_tile(ob, smem0 + sn * stage_bytes + a_bytes, nxt, K, tid);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  /* the last commit covers every MMA issued before it */
+  mbar_wait(smem_u32(&bars[(nkb - 1) % RR_TC_STAGES]), (uint32_t)(((nkb - 1) / RR_TC_STAGES) & 1));
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+  const int row = tile_m * RR_TC_BM + warp * 32 + lane;
+  const bool vec_d = (p.ldd % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.d) & 15) == 0);
+  const float *auxp = p.epi == 1 ? p.aux_out : (p.epi == 2 ? p.aux_in : nullptr);
+  const bool vec_aux = !auxp || ((p.ldaux % 4 == 0) && ((reinterpret_cast<uintptr_t>(auxp) & 15) == 0));
+  for (int j = 0; j < BN / 16; j++) {
+    uint32_t v[16];
+    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(j * 16);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    const int c0 = tile_n * BN + j * 16;
+    if (row >= p.m || c0 >= n_ext) continue;
+    if (c0 + 16 <= p.n && vec_d && vec_aux) {
+      /* full 16-column group: 16-byte loads / stores of this thread's row */
+      float o[16], z[16];
+#pragma unroll
+      for (int i = 0; i < 16; i++) o[i] = __uint_as_float(v[i]);
+      if (p.bias) {
+        const float4 *bp = reinterpret_cast<const float4 *>(p.bias + c0); /* c0 is a multiple of 16 */
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const float4 b4 = __ldg(bp + i);
+          o[4 * i] += b4.x; o[4 * i + 1] += b4.y; o[4 * i + 2] += b4.z; o[4 * i + 3] += b4.w;
+        }
+      }
+      if (p.epi == 1) {
+        if (p.aux_out) {
+          float4 *ap = reinterpret_cast<float4 *>(p.aux_out + (size_t)row * p.ldaux + c0);
+#pragma unroll
+          for (int i = 0; i < 4; i++) ap[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+        }
+#pragma unroll
+        for (int i = 0; i < 16; i++) o[i] *= rr_tc_sigmoid(o[i]);
+      } else if (p.epi == 2) {
+        const float4 *ap = reinterpret_cast<const float4 *>(p.aux_in + (size_t)row * p.ldaux + c0);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const float4 a4 = ap[i];
+          z[4 * i] = a4.x; z[4 * i + 1] = a4.y; z[4 * i + 2] = a4.z; z[4 * i + 3] = a4.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+          const float sg = rr_tc_sigmoid(z[i]);
+          o[i] *= sg * (1.f + z[i] * (1.f - sg));
+        }
+      }
+      float4 *dst = reinterpret_cast<float4 *>(p.d + (size_t)row * p.ldd + c0);
+#pragma unroll
+      for (int i = 0; i < 4; i++) dst[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; i++) {
+        const int c = c0 + i;
+        if (c < p.n) p.d[(size_t)row * p.ldd + c] = rr_tc_epilogue(p, row, c, __uint_as_float(v[i]));
+        else if (c == p.n && p.b_ones) p.ones_out[row] = __uint_as_float(v[i]);
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(ncols) : "memory");
+}
+
+}  // namespace rr_tc
+#endif

@@ -51,6 +51,8 @@ class PPOConfig:
     num_eval_envs: int = 128
     deterministic_eval: bool = False
     seed: int = 0
+    tc_learner: bool = False        # the two MLPs' forward / backward as 12 grouped tcgen05 GEMM launches (tc_learner.py) instead of
+                                    # autograd + cuBLAS (~95 launches); needs fused_loss
     fused_loss: bool = True         # loss + gradient w.r.t. the network outputs in two hand-written kernels (rr_ppo_loss)
     cuda_graph: bool = True         # replay the minibatch update (loss, backward, Adam) as one CUDA graph on CUDA devices
     graph_allreduce: bool = False   # several ranks: capture the NCCL all-reduce + Adam in the update graph too.  OFF: with torch 2.11 /
@@ -169,37 +171,46 @@ def compute_gae(L, truncation, termination, rewards, values, bootstrap, lambda_,
     return vs, adv
 
 
+def launch_ppo_loss(L, cfg, logits, baseline, bootstrap, mb, noise, grad_logits=None, grad_baseline=None):
+    """rr_ppo_loss on time-major logits [T, B, 2A], baseline [T, B], bootstrap [B]: returns (loss_partial [blocks, 3] -- column
+    sums / (T B) are the policy, value and entropy terms --, d total / d logits, d total / d baseline)."""
+    T, B = baseline.shape
+    A = logits.shape[-1] // 2
+    dev = logits.device
+    c = lambda x: x.detach().contiguous()
+    logits_c, baseline_c = c(logits), c(baseline)
+    ba, bb = ctypes.c_int32(), ctypes.c_int32()
+    _lib.check(L, L.rr_ppo_loss_blocks(T, B, ctypes.byref(ba), ctypes.byref(bb)))
+    scratch = torch.empty(3 * T * B, device=dev)
+    adv_partial = torch.empty(2 * ba.value, device=dev, dtype=torch.float64)
+    loss_partial = torch.empty((bb.value, 3), device=dev)
+    if grad_logits is None:
+        grad_logits, grad_baseline = torch.empty_like(logits_c), torch.empty_like(baseline_c)
+    keep = [logits_c, baseline_c, c(bootstrap), c(mb["raw_action"]), c(mb["log_prob"]), c(mb["reward"]), c(mb["discount"]),
+            c(mb["truncation"]), c(noise)]
+    a = _lib.RRPpoLossArgs()
+    a.T, a.B, a.A = T, B, A
+    for name, t in zip(("logits", "baseline", "bootstrap", "raw_action", "old_log_prob", "reward", "discount", "truncation",
+                        "noise"), keep):
+        assert t.dtype == torch.float32
+        setattr(a, name, t.data_ptr())
+    a.reward_scaling, a.discounting, a.gae_lambda = cfg.reward_scaling, cfg.discounting, cfg.gae_lambda
+    a.clipping_epsilon, a.entropy_cost, a.normalize_advantage = cfg.clipping_epsilon, cfg.entropy_cost, int(cfg.normalize_advantage)
+    a.scratch, a.adv_partial, a.loss_partial = scratch.data_ptr(), adv_partial.data_ptr(), loss_partial.data_ptr()
+    a.grad_logits, a.grad_baseline = grad_logits.data_ptr(), grad_baseline.data_ptr()
+    stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream) if logits.is_cuda else None
+    _lib.check(L, L.rr_ppo_loss(ctypes.byref(a), stream))
+    return loss_partial, grad_logits, grad_baseline
+
+
 class _FusedPPOLoss(torch.autograd.Function):
     """total loss of one minibatch through rr_ppo_loss; backward hands the kernel's analytic d loss / d (logits, baseline)
     to autograd, which continues through the two MLPs.  Returns (total, policy_loss, v_loss, entropy_loss)."""
 
     @staticmethod
     def forward(ctx, logits, baseline, bootstrap, mb, noise, cfg, L):
+        loss_partial, grad_logits, grad_baseline = launch_ppo_loss(L, cfg, logits, baseline, bootstrap, mb, noise)
         T, B = baseline.shape
-        A = logits.shape[-1] // 2
-        dev = logits.device
-        c = lambda x: x.detach().contiguous()
-        logits_c, baseline_c = c(logits), c(baseline)
-        ba, bb = ctypes.c_int32(), ctypes.c_int32()
-        _lib.check(L, L.rr_ppo_loss_blocks(T, B, ctypes.byref(ba), ctypes.byref(bb)))
-        scratch = torch.empty(3 * T * B, device=dev)
-        adv_partial = torch.empty(2 * ba.value, device=dev, dtype=torch.float64)
-        loss_partial = torch.empty((bb.value, 3), device=dev)
-        grad_logits, grad_baseline = torch.empty_like(logits_c), torch.empty_like(baseline_c)
-        keep = [logits_c, baseline_c, c(bootstrap), c(mb["raw_action"]), c(mb["log_prob"]), c(mb["reward"]), c(mb["discount"]),
-                c(mb["truncation"]), c(noise)]
-        a = _lib.RRPpoLossArgs()
-        a.T, a.B, a.A = T, B, A
-        for name, t in zip(("logits", "baseline", "bootstrap", "raw_action", "old_log_prob", "reward", "discount", "truncation",
-                            "noise"), keep):
-            assert t.dtype == torch.float32
-            setattr(a, name, t.data_ptr())
-        a.reward_scaling, a.discounting, a.gae_lambda = cfg.reward_scaling, cfg.discounting, cfg.gae_lambda
-        a.clipping_epsilon, a.entropy_cost, a.normalize_advantage = cfg.clipping_epsilon, cfg.entropy_cost, int(cfg.normalize_advantage)
-        a.scratch, a.adv_partial, a.loss_partial = scratch.data_ptr(), adv_partial.data_ptr(), loss_partial.data_ptr()
-        a.grad_logits, a.grad_baseline = grad_logits.data_ptr(), grad_baseline.data_ptr()
-        stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream) if logits.is_cuda else None
-        _lib.check(L, L.rr_ppo_loss(ctypes.byref(a), stream))
         terms = loss_partial.sum(0) / float(T * B)
         policy_loss, v_loss, entropy_loss = terms[0], terms[1], -cfg.entropy_cost * terms[2]
         ctx.save_for_backward(grad_logits, grad_baseline)
@@ -245,6 +256,10 @@ class PPO:
         self.gen.manual_seed(cfg.seed * 1000 + 17 + self.rank)
         self.env_steps = 0
         self._flat_grad = None
+        # tensor-core learner (tc_learner.py): built at the first loss_and_grads() call, when the minibatch shape is known
+        assert not cfg.tc_learner or cfg.fused_loss, "tc_learner needs fused_loss"
+        self._use_tc = bool(cfg.tc_learner)
+        self._tc = None
 
     # ---- acting -----------------------------------------------------------------------------------------------------
     def _norm(self, obs):
@@ -370,6 +385,36 @@ class PPO:
         return total, dict(total_loss=total.detach(), policy_loss=policy_loss.detach(), v_loss=v_loss.detach(),
                            entropy_loss=entropy_loss.detach())
 
+    def loss_and_grads(self, mb: Dict[str, torch.Tensor], zero_grad_to_none: bool = False):
+        """Loss of one minibatch and its gradient in every parameter's .grad.  Autograd through cuBLAS, or (cfg.tc_learner) the
+        hand-written forward / backward on the tcgen05 GEMM kernel: 12 grouped launches + the two loss kernels."""
+        if not self._use_tc:
+            total, metrics = self.loss(mb)
+            self.opt.zero_grad(set_to_none=zero_grad_to_none)
+            total.backward()
+            return metrics
+        cfg = self.cfg
+        obs, nxt = self._norm_mb(mb["observation"]), self._norm_mb(mb["next_observation_last"])
+        T, b = obs.shape[0], obs.shape[1]
+        if self._tc is None or self._tc.x.shape[0] != T * b:
+            from .tc_learner import TcLearner
+            self._tc = TcLearner(self.env._L, self.policy, self.value, T * b, b, self.device)
+        tc = self._tc
+        if obs.data_ptr() != tc.x.data_ptr():
+            tc.x.copy_(obs.reshape(T * b, -1))
+        if nxt.data_ptr() != tc.xb.data_ptr():
+            tc.xb.copy_(nxt.reshape(b, -1))
+        tc.forward()
+        noise = mb.get("entropy_noise")
+        if noise is None:
+            noise = torch.randn(mb["raw_action"].shape, device=obs.device, generator=self.gen)
+        loss_partial, _, _ = launch_ppo_loss(self.env._L, cfg, tc.logits.view(T, b, -1), tc.baseline.view(T, b), tc.bootstrap.view(b),
+                                             mb, noise, tc.grad_logits, tc.grad_baseline)
+        tc.backward()
+        terms = loss_partial.sum(0) / float(T * b)
+        policy_loss, v_loss, entropy_loss = terms[0], terms[1], -cfg.entropy_cost * terms[2]
+        return dict(total_loss=policy_loss + v_loss + entropy_loss, policy_loss=policy_loss, v_loss=v_loss, entropy_loss=entropy_loss)
+
     def _allreduce_grads(self):
         """lax.pmean(grads): one flat fp32 bucket (2.53 MB for the rodent networks) per minibatch over NCCL."""
         if self.world == 1:
@@ -397,6 +442,12 @@ class PPO:
                                            else (cfg.batch_size,) + tuple(v.shape[1:]), device=self.device, dtype=v.dtype)
                             for k, v in data.items()}
             self._static["entropy_noise"] = torch.empty((cfg.unroll_length, cfg.batch_size, self.env.action_size), device=self.device)
+            if self._use_tc:  # gather the minibatch straight into the tensor-core learner's input buffers
+                from .tc_learner import TcLearner
+                T, b = data["observation"].shape[0], cfg.batch_size
+                self._tc = TcLearner(self.env._L, self.policy, self.value, T * b, b, self.device)
+                self._static["observation"] = self._tc.x.view(T, b, -1)
+                self._static["next_observation_last"] = self._tc.xb
         st = self._static
         for k, v in data.items():
             torch.index_select(v, 1 if k != "next_observation_last" else 0, idx, out=st[k])
@@ -406,9 +457,7 @@ class PPO:
             side = torch.cuda.Stream(self.device)
             side.wait_stream(torch.cuda.current_stream(self.device))
             with torch.cuda.stream(side):
-                total, metrics = self.loss(st)
-                self.opt.zero_grad(set_to_none=True)
-                total.backward()
+                metrics = self.loss_and_grads(st, zero_grad_to_none=True)
                 self._allreduce_grads()
                 self.opt.step()
             torch.cuda.current_stream(self.device).wait_stream(side)
@@ -416,11 +465,11 @@ class PPO:
             return metrics
         if self._graph is None:
             g = torch.cuda.CUDAGraph()
-            self.opt.zero_grad(set_to_none=True)
+            if not self._use_tc:
+                self.opt.zero_grad(set_to_none=True)
             in_graph = self.world == 1 or self.cfg.graph_allreduce
             with torch.cuda.graph(g):
-                total, metrics = self.loss(st)
-                total.backward()
+                metrics = self.loss_and_grads(st, zero_grad_to_none=True)
                 if in_graph:
                     self._allreduce_grads()  # NCCL all-reduce of the flat bucket, captured with the rest (no-op on one rank)
                     self.opt.step()
@@ -456,9 +505,7 @@ class PPO:
                     metrics = self._update_graphed(data, idx)
                     continue
                 mb = {k: (v[:, idx] if k != "next_observation_last" else v[idx]) for k, v in data.items()}
-                total, metrics = self.loss(mb)
-                self.opt.zero_grad(set_to_none=False)
-                total.backward()
+                metrics = self.loss_and_grads(mb)
                 self._allreduce_grads()
                 self.opt.step()
         if self._use_graph:

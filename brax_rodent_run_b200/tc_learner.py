@@ -1,0 +1,108 @@
+"""Forward and hand-written backward of the PPO learner's policy / value MLPs on the tcgen05 GEMM kernel (tc_gemm.py).
+
+Replaces, for one minibatch, what autograd + cuBLAS did in ~95 launches (brax: `jax.grad(compute_ppo_loss)` inside ppo.train,
+brax_rodent_run_ppo.py:97-114, 200) by 12 grouped launches:
+  forward   6: layer l of the policy net, the value net and the bootstrap value net (next observation) in ONE launch each;
+               bias + SiLU fused, the pre-activations kept for the backward pass
+  loss      2: rr_ppo_loss (d loss / d logits, d loss / d baseline)
+  dgrad     5: dZ_{l-1} = (dZ_l W_l) * silu'(Z_{l-1}) for both nets per launch (W read MN-major: no transposed copy)
+  wgrad     1: all eleven dW_l = dZ_l' X_l in one launch, db_l as the product's extra "ones" column, written straight into the
+               parameters' .grad tensors
+The parameters stay ordinary nn.Linear weights (acting, export and the optimizer are unchanged).
+"""
+from __future__ import annotations
+
+from typing import List
+
+import torch
+from torch import nn
+
+from . import tc_gemm
+from .tc_gemm import EPI_DSILU, EPI_LINEAR, EPI_SILU, TcGroup, problem
+
+
+def _linears(net: nn.Sequential) -> List[nn.Linear]:
+    return [m for m in net if isinstance(m, nn.Linear)]
+
+
+class TcLearner:
+    def __init__(self, L, policy: nn.Sequential, value: nn.Sequential, rows: int, boot_rows: int, device):
+        self.L, self.device = L, torch.device(device)
+        self.lp, self.lv = _linears(policy), _linears(value)
+        M, Mb, dev = rows, boot_rows, self.device
+        k0 = self.lp[0].in_features
+        assert self.lv[0].in_features == k0
+        new = lambda r, c: torch.zeros(r, c, device=dev)
+        self.x, self.xb = new(M, k0), new(Mb, k0)
+        # activations (h), pre-activations (z) and their gradients (dz) of the hidden layers; the heads' outputs
+        self.hp = [new(M, l.out_features) for l in self.lp[:-1]]
+        self.zp = [torch.zeros_like(h) for h in self.hp]
+        self.dzp = [torch.zeros_like(h) for h in self.hp]
+        self.hv = [new(M, l.out_features) for l in self.lv[:-1]]
+        self.zv = [torch.zeros_like(h) for h in self.hv]
+        self.dzv = [torch.zeros_like(h) for h in self.hv]
+        self.hb = [new(Mb, l.out_features) for l in self.lv[:-1]]
+        self.logits, self.grad_logits = new(M, self.lp[-1].out_features), new(M, self.lp[-1].out_features)
+        self.baseline, self.grad_baseline = new(M, 1), new(M, 1)
+        self.bootstrap = new(Mb, 1)
+        for lin in self.lp + self.lv:  # static gradient tensors: the wgrad launch overwrites them completely
+            lin.weight.grad = torch.zeros_like(lin.weight)
+            lin.bias.grad = torch.zeros_like(lin.bias)
+
+        def fwd(lins, l, inp, h, z, out):
+            lin, last = lins[l], l == len(lins) - 1
+            if last:
+                return problem(inp, lin.weight.data, out, bias=lin.bias.data, epi=EPI_LINEAR)
+            return problem(inp, lin.weight.data, h[l], bias=lin.bias.data, epi=EPI_SILU, aux_out=z[l] if z is not None else None)
+
+        self.fwd_groups = []
+        for l in range(max(len(self.lp), len(self.lv))):
+            probs = []
+            if l < len(self.lp):
+                probs.append(fwd(self.lp, l, self.x if l == 0 else self.hp[l - 1], self.hp, self.zp, self.logits))
+            if l < len(self.lv):
+                probs.append(fwd(self.lv, l, self.x if l == 0 else self.hv[l - 1], self.hv, self.zv, self.baseline))
+                probs.append(fwd(self.lv, l, self.xb if l == 0 else self.hb[l - 1], self.hb, None, self.bootstrap))
+            self.fwd_groups.append(TcGroup(L, probs, dev))
+
+        # dgrad: walk both nets from the heads down; step s handles layer (n - 1 - s) of each net that still has a hidden input
+        def dgrad_chain(lins, dz, z, g_head):
+            chain = []
+            for l in range(len(lins) - 1, 0, -1):  # dZ_{l-1} from dZ_l
+                dz_l = g_head if l == len(lins) - 1 else dz[l]
+                chain.append(problem(dz_l, lins[l].weight.data, dz[l - 1], b_t=True, epi=EPI_DSILU, aux_in=z[l - 1]))
+            return chain
+
+        cp, cv = dgrad_chain(self.lp, self.dzp, self.zp, self.grad_logits), dgrad_chain(self.lv, self.dzv, self.zv, self.grad_baseline)
+        self.dgrad_groups = []
+        # align the chains at their ends so that both finish in the last launch (the value net is one layer deeper)
+        steps = max(len(cp), len(cv))
+        for s in range(steps):
+            probs = []
+            ip, iv = s - (steps - len(cp)), s - (steps - len(cv))
+            if ip >= 0:
+                probs.append(cp[ip])
+            if iv >= 0:
+                probs.append(cv[iv])
+            self.dgrad_groups.append(TcGroup(L, probs, dev))
+
+        def wgrad(lins, dz, h, g_head, l):
+            dz_l = g_head if l == len(lins) - 1 else dz[l]
+            inp = self.x if l == 0 else h[l - 1]
+            return problem(dz_l, inp, lins[l].weight.grad, a_t=True, b_t=True, ones_out=lins[l].bias.grad)
+
+        probs = [wgrad(self.lv, self.dzv, self.hv, self.grad_baseline, l) for l in range(len(self.lv))]
+        probs += [wgrad(self.lp, self.dzp, self.hp, self.grad_logits, l) for l in range(len(self.lp))]
+        self.wgrad_group = TcGroup(L, probs, dev)
+        self.launches_per_update = len(self.fwd_groups) + len(self.dgrad_groups) + 1
+
+    def forward(self) -> None:
+        """x, xb -> logits [M, 2A], baseline [M, 1], bootstrap [Mb, 1] (+ the activations the backward pass needs)."""
+        for g in self.fwd_groups:
+            g.launch()
+
+    def backward(self) -> None:
+        """grad_logits, grad_baseline -> .grad of every weight and bias."""
+        for g in self.dgrad_groups:
+            g.launch()
+        self.wgrad_group.launch()

@@ -143,6 +143,32 @@ int rr_ppo_loss_blocks(int32_t T, int32_t B, int32_t *blocks_a, int32_t *blocks_
 int rr_ppo_loss(const rr_ppo_loss_args *args, void *stream);
 
 
+/* Grouped TF32 tensor-core GEMM with fused epilogues: the contractions of the PPO learner (brax ppo.train's policy / value MLPs
+ * under jax.grad, brax_rodent_run_ppo.py:97-114, 200).  One launch runs a LIST of problems D = epi(A B' + bias), A logical
+ * [m x k], B logical [n x k], fp32 in memory, TF32 products with fp32 accumulation in tensor memory (tcgen05.mma kind::tf32,
+ * one 128 x bn tile per CTA, operands staged by cp.async straight into the UMMA canonical no-swizzle layouts).
+ *   a_mn / b_mn   0: K-major, element (r, kk) at r * ld + kk;   1: MN-major, element (r, kk) at kk * ld + r
+ *                 (so X W', dY W and dY' X all run without a transposed copy)
+ *   epi           0: D = acc + bias
+ *                 1: z = acc + bias; aux_out (if given) = z; D = silu(z)
+ *                 2: D = (acc + bias) * silu'(aux_in)         (dgrad through the previous layer's activation)
+ *   b_ones        B gets a virtual extra row n of ones (MN-major B only): column n of the product, the sum of A over k --
+ *                 the bias gradient when A = dY' -- goes to ones_out[m]
+ * rr_tc_plan validates a HOST array and fills bn / tile_start / tiles_n; rr_tc_launch takes a DEVICE copy of the planned array
+ * (so that the launch is capturable in a CUDA graph).  All matrices are DEVICE pointers. */
+typedef struct rr_tc_problem {
+  const float *a, *b;
+  float *d;
+  const float *bias, *aux_in;
+  float *aux_out, *ones_out;
+  int32_t m, n, k, lda, ldb, ldd, ldaux;
+  int32_t a_mn, b_mn, epi, b_ones;
+  int32_t bn, tile_start, tiles_n; /* filled by rr_tc_plan */
+  int32_t reserved[4];
+} rr_tc_problem;
+int rr_tc_plan(rr_tc_problem *host_problems, int32_t count, int32_t *total_tiles, int32_t *smem_bytes);
+int rr_tc_launch(const rr_tc_problem *device_problems, int32_t count, int32_t total_tiles, int32_t smem_bytes, void *stream);
+
 /* Parity-test hooks: per-environment dump of forward-pass intermediates (tests only). */
 int rr_debug_field(const rr_model *m, const char *name, int32_t *offset, int32_t *count);
 int rr_env_set_debug(rr_env *e, float *dbg /* DEVICE [B, debug_stride] or null */);

@@ -218,4 +218,13 @@ static int rrb_launch_ppo_loss(const RRPpoLossArgs &a, void *) {
   return 0;
 }
 
+/* the learner's grouped GEMM: plain loops with the contract of rr_tc_problem ("device" pointers are host pointers) */
+#define RR_TC_HD static inline
+#include "../../brax_rodent_run_b200/csrc/rr_tc_gemm.h"
+static int rrb_tc_smem_max() { return RR_TC_STAGES * (RR_TC_BM + 128) * RR_TC_BK * 4; }
+static int rrb_tc_launch(const rr_tc_problem *probs, int count, int, int, void *) {
+  for (int i = 0; i < count; i++) rr_tc_reference(probs[i]);
+  return 0;
+}
+
 #include "../../brax_rodent_run_b200/csrc/rr_api_impl.inl"

@@ -357,3 +357,110 @@ def test_rollout_graph_matches_eager_unroll():
 def dataclasses_asdict(cfg):
     import dataclasses
     return dataclasses.asdict(cfg)
+
+
+def _compare_tc_with_autograd(agent, mb, tol):
+    """loss_and_grads through the hand-written forward / backward (tc_learner.py on rr_tc_launch) against autograd."""
+    outs = []
+    for use_tc in (False, True):
+        agent._use_tc = use_tc
+        if not use_tc:
+            for p in agent.params:
+                p.grad = None
+        metrics = agent.loss_and_grads(mb)
+        outs.append(({k: float(v) for k, v in metrics.items()}, torch.cat([p.grad.reshape(-1) for p in agent.params]).cpu().clone(),
+                     [p.grad.detach().cpu().clone() for p in agent.params]))
+    (m0, g0, l0), (m1, g1, l1) = outs
+    for k in m0:
+        assert abs(m0[k] - m1[k]) <= tol * max(1.0, abs(m0[k])), (k, m0[k], m1[k])
+    assert float(g0.abs().max()) > 0
+    for i, (a, b) in enumerate(zip(l0, l1)):     # per parameter tensor, relative to its own scale
+        assert a.shape == b.shape
+        assert float((a - b).abs().max()) <= tol * max(float(a.abs().max()), 1e-3 * float(g0.abs().max())), (i, a.shape)
+
+
+def test_tc_learner_matches_autograd_on_emulator(emu_lib):
+    agent, mb = _loss_case(tiny_env(emu_lib), "cpu", seed=3, T=3, B=5)
+    _compare_tc_with_autograd(agent, mb, 2e-4)
+    assert agent._tc.launches_per_update == 3 + 2 + 1    # TINY: 3 forward layers, 2 dgrad steps, one wgrad launch
+
+
+def test_training_step_with_tc_learner_on_emulator(emu_lib):
+    """The whole training step (eager path on the CPU) with the tensor-core learner's launch lists on the emulator backend."""
+    from brax_rodent_run_b200.ppo import PPO, PPOConfig
+    outs = []
+    for tc in (False, True):
+        cfg = PPOConfig(**dict(TINY, tc_learner=tc))
+        env = tiny_env(emu_lib).wrap_for_training(cfg.episode_length)
+        agent = PPO(env, cfg)
+        state = env.reset(0)
+        state, metrics = agent.training_step(state)
+        outs.append(torch.cat([p.detach().reshape(-1) for p in agent.params]))
+    assert float((outs[0] - outs[1]).abs().max()) < 1e-4
+
+
+@pytest.mark.gpu
+def test_tc_learner_matches_autograd_on_gpu():
+    """README minibatch shape (10 x 512 rows, 1264 features, 256-wide value net) through the tcgen05 kernel; both sides use TF32
+    products, so the comparison is at TF32 accuracy."""
+    from brax_rodent_run_b200.env import Rodent
+    from brax_rodent_run_b200.ppo import PPO, PPOConfig
+    env = Rodent(synthetic_track(), num_envs=2, device="cuda:0", model=load_asset("rodent_0"), iterations=1, ls_iterations=1, n_frames=1)
+    cfg = PPOConfig(num_envs=2, batch_size=2, num_minibatches=2, unroll_length=2, cuda_graph=False, tf32=False)
+    agent = PPO(env, cfg)
+    _, mb = _loss_case(env, "cuda:0", seed=2, T=10, B=512)
+    agent._batch_is_normalized = True
+    _compare_tc_with_autograd(agent, mb, 1e-2)
+
+
+@pytest.mark.gpu
+def test_graphed_tc_update_matches_eager_autograd_update():
+    """The captured update with the tensor-core learner applies (to TF32 accuracy) the same parameter update as the eager autograd
+    update on the same minibatch, noise, parameters and Adam state."""
+    from brax_rodent_run_b200.env import Rodent
+    from brax_rodent_run_b200.ppo import PPO, PPOConfig
+    cfg = PPOConfig(num_envs=64, batch_size=16, num_minibatches=8, unroll_length=4, num_updates_per_batch=2, episode_length=50,
+                    num_timesteps=1, policy_hidden=(32, 32), value_hidden=(64, 64), tf32=False, cuda_graph=True, tc_learner=True)
+    env = Rodent(synthetic_track(), num_envs=64, device="cuda:0", model=load_asset("rodent_0"), iterations=4, ls_iterations=4,
+                 terminate_when_unhealthy=False).wrap_for_training(cfg.episode_length)
+    agent = PPO(env, cfg)
+    state = env.reset(0)
+    state, metrics = agent.training_step(state)
+    assert agent._graph is not None and agent._tc is not None
+    assert all(math.isfinite(float(v)) for v in metrics.values())
+    chunks = []
+    for _ in range(cfg.batch_size * cfg.num_minibatches // cfg.num_envs):
+        state, d = agent.unroll(state)
+        chunks.append(d)
+    data = {k: torch.cat([c[k] for c in chunks], dim=1 if k != "next_observation_last" else 0) for k in chunks[0]}
+    data["observation"] = agent._norm(data["observation"])
+    data["next_observation_last"] = agent._norm(data["next_observation_last"])
+    agent._batch_is_normalized = True
+    idx = torch.arange(3, 3 + cfg.batch_size, device="cuda:0")
+    opt_tensors = [t for st in agent.opt.state.values() for t in st.values() if torch.is_tensor(t)]
+    saved = [t.clone() for t in agent.params + opt_tensors]
+    gen_state = agent.gen.get_state()
+    m_graph = {k: float(v) for k, v in agent._update_graphed(data, idx).items()}
+    d_graph = torch.cat([(p.detach() - v).reshape(-1) for p, v in zip(agent.params, saved)]).cpu()
+    with torch.no_grad():
+        for t, v in zip(agent.params + opt_tensors, saved):
+            t.copy_(v)
+    agent.gen.set_state(gen_state)
+    st = agent._static
+    st["entropy_noise"].normal_(generator=agent.gen)
+    agent._use_tc = False
+    tc_grads = [p.grad for p in agent.params]
+    for p in agent.params:
+        p.grad = None
+    total, m = agent.loss(st)
+    total.backward()
+    agent.opt.step()
+    for p, g in zip(agent.params, tc_grads):
+        p.grad = g
+    agent._use_tc = True
+    d_eager = torch.cat([(p.detach() - v).reshape(-1) for p, v in zip(agent.params, saved)]).cpu()
+    for k in m:
+        assert abs(m_graph[k] - float(m[k])) <= 2e-3 * max(1.0, abs(float(m[k]))), (k, m_graph[k], float(m[k]))
+    assert float(d_eager.abs().max()) > 0.1 * cfg.learning_rate
+    # Adam's normalised step amplifies relative gradient error where the gradient is tiny: compare in the mean
+    assert float((d_graph - d_eager).abs().mean()) < 0.05 * float(d_eager.abs().mean())

@@ -1,0 +1,91 @@
+"""rr_tc_plan / rr_tc_launch (include/rr_b200.h): the learner's grouped GEMM with fused epilogues against plain torch.
+
+On the CPU the emulator backend runs the contract's plain loops (the problem-list logic, majors, epilogues, the bias-gradient
+column); on a GPU the same cases go through the tcgen05 kernel (TF32 products, fp32 accumulation: tolerance 2e-3 relative to
+the magnitude of the result, as cuBLAS's TF32 path)."""
+import pytest
+import torch
+
+from brax_rodent_run_b200 import _lib, tc_gemm
+from conftest import backend_params, has_cuda
+
+
+def _setup(backend, emu_lib):
+    if backend == "emu":
+        return _lib.load(emu_lib), torch.device("cpu"), 1e-5
+    if not has_cuda():
+        pytest.skip("no CUDA device")
+    return _lib.load(), torch.device("cuda:0"), 2e-3
+
+
+def _silu_grad(z):
+    s = torch.sigmoid(z)
+    return s * (1 + z * (1 - s))
+
+
+def _close(got, want, tol, scale=None):
+    """`scale`: magnitude of the summed products (TF32 rounds every product; a sum that cancels keeps their absolute error)."""
+    scale = max(float(want.abs().max()), 1e-6, scale or 0.0)
+    err = float((got - want).abs().max()) / scale
+    assert err <= tol, err
+
+
+# (m, n, k): tile-aligned, ragged in every direction, the value head (n = 1), the policy head (n = 60), k not a multiple of 4
+SHAPES = [(128, 64, 32), (256, 256, 1264), (200, 60, 32), (130, 1, 256), (77, 33, 50), (512, 256, 256), (5, 7, 3)]
+
+
+@pytest.mark.parametrize("backend", backend_params())
+@pytest.mark.parametrize("m,n,k", SHAPES)
+def test_forward_linear_and_silu(backend, emu_lib, m, n, k):
+    L, dev, tol = _setup(backend, emu_lib)
+    g = torch.Generator().manual_seed(m * 1000 + n * 10 + k)
+    x = torch.randn(m, k, generator=g).to(dev)
+    w = (torch.randn(n, k, generator=g) / k ** 0.5).to(dev)
+    b = torch.randn(n, generator=g).to(dev)
+    y0, y1, z1 = (torch.full((m, n), float("nan"), device=dev) for _ in range(3))
+    grp = tc_gemm.TcGroup(L, [tc_gemm.problem(x, w, y0, bias=b),
+                              tc_gemm.problem(x, w, y1, bias=b, epi=tc_gemm.EPI_SILU, aux_out=z1)], dev)
+    grp.launch()
+    want = x.double() @ w.double().T + b.double()
+    _close(y0.double(), want, tol)
+    _close(z1.double(), want, tol)
+    _close(y1.double(), torch.nn.functional.silu(want), tol)
+
+
+@pytest.mark.parametrize("backend", backend_params())
+@pytest.mark.parametrize("m,n,k", SHAPES)
+def test_dgrad_and_wgrad(backend, emu_lib, m, n, k):
+    """dX = (dY W) * silu'(Z) with W read MN-major; dW = dY' X and db = dY' 1 with both operands MN-major."""
+    L, dev, tol = _setup(backend, emu_lib)
+    g = torch.Generator().manual_seed(m * 1000 + n * 10 + k + 1)
+    x = torch.randn(m, k, generator=g).to(dev)
+    z = torch.randn(m, k, generator=g).to(dev)
+    w = (torch.randn(n, k, generator=g) / n ** 0.5).to(dev)
+    dy = torch.randn(m, n, generator=g).to(dev)
+    dx = torch.full((m, k), float("nan"), device=dev)
+    dw = torch.full((n, k), float("nan"), device=dev)
+    db = torch.full((n,), float("nan"), device=dev)
+    grp = tc_gemm.TcGroup(L, [tc_gemm.problem(dy, w, dx, b_t=True, epi=tc_gemm.EPI_DSILU, aux_in=z),
+                              tc_gemm.problem(dy, x, dw, a_t=True, b_t=True, ones_out=db)], dev)
+    grp.launch()
+    _close(dx.double(), (dy.double() @ w.double()) * _silu_grad(z.double()), tol)
+    _close(dw.double(), dy.double().T @ x.double(), tol)
+    _close(db.double(), dy.double().sum(0), tol, scale=float(dy.abs().sum(0).max()) / 10)
+
+
+@pytest.mark.parametrize("backend", backend_params())
+def test_strided_views_and_errors(backend, emu_lib):
+    """Operands may be column slices of wider arrays (leading dimension > row length); bad problems raise ValueError."""
+    L, dev, tol = _setup(backend, emu_lib)
+    g = torch.Generator().manual_seed(5)
+    big = torch.randn(96, 300, generator=g).to(dev)
+    x, w = big[:, 4:132], torch.randn(48, 128, generator=g).to(dev)
+    out = torch.zeros(96, 100, device=dev)
+    grp = tc_gemm.TcGroup(L, [tc_gemm.problem(x, w, out[:, 52:100])], dev)
+    grp.launch()
+    _close(out[:, 52:100].double(), x.double() @ w.double().T, tol)
+    assert float(out[:, :52].abs().max()) == 0.0
+    with pytest.raises(ValueError):
+        p = tc_gemm.problem(x, w, out[:, 52:100])
+        p["epi"] = 2  # no aux_in
+        tc_gemm.TcGroup(L, [p], dev)

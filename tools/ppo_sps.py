@@ -9,11 +9,12 @@ from brax_rodent_run_b200 import ppo
 ap = argparse.ArgumentParser()
 ap.add_argument("--train-steps", type=int, default=3)
 ap.add_argument("--envs", type=int, default=2048)
+ap.add_argument("--tc-learner", type=int, default=None, help="1 / 0: tensor-core learner on / off (default: PPOConfig's)")
 a = ap.parse_args()
 track = np.stack([0.002 * np.arange(250), np.zeros(250), np.full(250, 0.055)], 1).astype(np.float32)
 env = Rodent(track, num_envs=a.envs, device="cuda:0", model="rodent_0", iterations=8, ls_iterations=8,
              terminate_when_unhealthy=False, kinematics_outputs=False)
-cfg = ppo.PPOConfig(num_envs=a.envs)
+cfg = ppo.PPOConfig(num_envs=a.envs) if a.tc_learner is None else ppo.PPOConfig(num_envs=a.envs, tc_learner=bool(a.tc_learner))
 agent = ppo.PPO(env.wrap_for_training(cfg.episode_length), cfg)
 state = env.reset(0)
 state, _ = agent.training_step(state)  # warm-up (allocator, cuBLAS handles)
@@ -35,5 +36,5 @@ dt = time.perf_counter() - t0
 steps = agent.env_steps - e0
 print(json.dumps({"metric": "PPO train SPS", "value": steps / dt, "unit": "env-steps/s", "envs": a.envs, "train_steps": a.train_steps,
                   "env_steps_per_train_step": steps // a.train_steps, "s_per_train_step": dt / a.train_steps,
-                  "rollout_s": t_roll, "learner_s": dt / a.train_steps - t_roll,
+                  "tc_learner": cfg.tc_learner, "rollout_s": t_roll, "learner_s": dt / a.train_steps - t_roll,
                   "config": "README: batch 512, 64 minibatches, unroll 10, 8 epochs, CG 8/8, normalize obs"}))
