@@ -3,8 +3,8 @@
  * include/rr_b200.h for the semantics; the host-side reference of the same semantics is rr_tc_reference() below (used by the
  * emulator backend under tests/emu so that the Python learner's problem lists can be checked on the CPU).
  *
- * One CTA (128 threads) owns one 128 x bn output tile:
- *   - all four warps stream the k-blocks (32 wide) of A and B with cp.async, 16 bytes at a time, straight into the UMMA
+ * One CTA (256 threads) owns one 128 x bn output tile:
+ *   - four producer warps stream the k-blocks (32 wide) of A and B with cp.async, 16 bytes at a time, straight into the UMMA
  *     canonical shared-memory layouts:
  *         K-major operand, no swizzle: core matrix = 8 rows x 16 bytes, contiguous 128 B; core (row / 8, k / 4) at
  *             (row / 8) * 1024 + (k / 4) * 128                                                     [SBO 1024, LBO 128]
@@ -13,9 +13,10 @@
  *             sits at unit u ^ (k % 4); atom (row / 32, k / 4) at (row / 32) * 4096 + (k / 4) * 512   [LBO 4096, SBO 512]
  *     so row-major X, W (K-major for X W') and the same arrays read "transposed" (MN-major, for dY W and dY' X) need no copy;
  *     ragged edges are zero-filled in shared memory, a virtual row of ones gives the bias gradient;
- *   - RR_TC_STAGES-deep ring: cp.async.wait_group -> fence.proxy.async -> __syncthreads -> thread 0 issues the four
- *     tcgen05.mma (K = 8 each) of the stage and tcgen05.commit's to the stage's mbarrier, which the loaders wait on before
- *     they overwrite the stage;
+ *   - RR_TC_STAGES-deep ring, warp-specialised: producer warp w owns stage w (copies, cp.async.wait_group 0,
+ *     fence.proxy.async, arrive on the stage's "full" mbarrier); one thread of warp 4 waits for "full", issues the four
+ *     tcgen05.mma (K = 8 each) of the stage and tcgen05.commit's to the stage's "empty" mbarrier, which the producer waits on
+ *     before it overwrites the stage;
  *   - epilogue: each warp reads its 32 TMEM lanes (= rows) with tcgen05.ld 32x32b.x16, applies the epilogue and stores rows.
  */
 #pragma once
@@ -27,7 +28,7 @@
 #define RR_TC_BM 128
 #define RR_TC_BK 32
 #define RR_TC_STAGES 4
-#define RR_TC_THREADS 128
+#define RR_TC_THREADS 256
 
 RR_TC_HD float rr_tc_sigmoid(float z) { return 1.f / (1.f + expf(-z)); }
 RR_TC_HD float rr_tc_epilogue(const rr_tc_problem &p, int row, int col, float acc) {
@@ -90,6 +91,13 @@ __device__ __forceinline__ void cp_async4(uint32_t dst, const void *src) {
 __device__ __forceinline__ void st_shared_f32(uint32_t dst, float v) {
   asm volatile("st.shared.f32 [%0], %1;" ::"r"(dst), "f"(v) : "memory");
 }
+/* round to nearest TF32: outputs that are only ever read as MMA operands again (activations, their gradients) are stored
+ * pre-rounded, so that the tensor core's truncation of the operand is exact and the rounding error stays unbiased */
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
 __device__ __forceinline__ void st_shared_zero16(uint32_t dst) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "f"(0.f) : "memory");
 }
@@ -106,56 +114,110 @@ struct Operand {
   int rows, ld, mn, row0, tile_rows, fast, ones_row; /* ones_row: global row index that reads as 1 (or -1) */
 };
 
-/* one k-block of one operand tile into shared memory; every thread handles chunks tid, tid + 128, ... (a chunk = one 16-byte
- * line of a core matrix) */
-__device__ __forceinline__ void load_tile(const Operand &o, uint32_t sbase, int kb, int K, int tid) {
-  const int nchunk = o.tile_rows * (RR_TC_BK / 4);
-  const int kbase = kb * RR_TC_BK;
+/* Chunk c (one 16-byte line) of an operand tile at k-block 0: shared-memory offset, global element offset, how many of its 4
+ * elements are inside the matrix when the k index is (rows4; for K-major operands: 4 if the row is), the k index and the
+ * position of the virtual "one" among the 4 elements (-1: none). */
+struct ChunkGeom { uint32_t dst; size_t src; int rows4, k, one; };
+__device__ __forceinline__ ChunkGeom chunk_geom(const Operand &o, int c) {
+  ChunkGeom g;
   if (!o.mn) {
-    for (int c = tid; c < nchunk; c += RR_TC_THREADS) {
-      const int l = c & 7, kc = (c >> 3) & 7, cr = c >> 6;
-      const int row = o.row0 + cr * 8 + l, k0 = kbase + kc * 4;
-      const uint32_t dst = sbase + cr * 1024 + kc * 128 + l * 16;
-      int cnt = K - k0;
-      cnt = row < o.rows ? (cnt > 4 ? 4 : cnt) : 0;
-      const float *src = o.base + (size_t)row * o.ld + k0;
-      if (cnt == 4 && o.fast) cp_async16(dst, src);
-      else if (cnt <= 0) st_shared_zero16(dst);
-      else {
-#pragma unroll
-        for (int e = 0; e < 4; e++) {
-          if (e < cnt) cp_async4(dst + 4 * e, src + e);
-          else st_shared_f32(dst + 4 * e, 0.f);
-        }
-      }
-    }
+    const int l = c & 7, kc = (c >> 3) & 7, cr = c >> 6;
+    const int row = o.row0 + cr * 8 + l;
+    g.k = kc * 4;
+    g.dst = cr * 1024 + kc * 128 + l * 16;
+    g.src = (size_t)row * o.ld + g.k;
+    g.rows4 = row < o.rows ? 4 : 0;
+    g.one = -1;
   } else {
     /* a warp's 32 consecutive chunks = one 512-byte swizzle atom: 4 k-lines of 128 contiguous bytes (32 rows) each */
-    const int nchunk_mn = ((o.tile_rows + 31) >> 5) * 32 * (RR_TC_BK / 4);
-    for (int c = tid; c < nchunk_mn; c += RR_TC_THREADS) {
-      const int j = c & 7, kr = (c >> 3) & 3, rest = c >> 5, kq = rest & 7, mb = rest >> 3;
-      const int k = kbase + kq * 4 + kr, r0 = o.row0 + mb * 32 + j * 4;
-      const uint32_t dst = sbase + mb * 4096 + kq * 512 + kr * 128 + ((((j >> 1) ^ kr) << 5) | ((j & 1) << 4));
-      int cnt = o.rows - r0;
-      cnt = k < K ? (cnt > 4 ? 4 : cnt) : 0;
-      const float *src = o.base + (size_t)k * o.ld + r0;
-      const int one = (k < K && o.ones_row >= r0 && o.ones_row < r0 + 4) ? o.ones_row - r0 : -1;
-      if (cnt == 4 && o.fast) cp_async16(dst, src);
-      else if (cnt <= 0 && one < 0) st_shared_zero16(dst);
-      else {
+    const int j = c & 7, kr = (c >> 3) & 3, rest = c >> 5, kq = rest & 7, mb = rest >> 3;
+    const int r0 = o.row0 + mb * 32 + j * 4;
+    g.k = kq * 4 + kr;
+    g.dst = mb * 4096 + kq * 512 + kr * 128 + ((((j >> 1) ^ kr) << 5) | ((j & 1) << 4));
+    g.src = (size_t)g.k * o.ld + r0;
+    const int cnt = o.rows - r0;
+    g.rows4 = cnt > 4 ? 4 : (cnt < 0 ? 0 : cnt);
+    g.one = (o.ones_row >= r0 && o.ones_row < r0 + 4) ? o.ones_row - r0 : -1;
+  }
+  return g;
+}
+__device__ __forceinline__ int tile_chunks(const Operand &o) {
+  return (o.mn ? ((o.tile_rows + 31) >> 5) * 32 : o.tile_rows) * (RR_TC_BK / 4);
+}
+
+/* one k-block of one operand tile into shared memory, any shape: ragged edges are zero-filled, unaligned operands go 4 bytes
+ * at a time; the calling warp's lanes handle chunks lane, lane + 32, ... */
+__device__ __forceinline__ void load_tile(const Operand &o, uint32_t sbase, int kb, int K, int lane) {
+  const int nchunk = tile_chunks(o), kbase = kb * RR_TC_BK;
+  const size_t kstep = (size_t)kbase * (o.mn ? o.ld : 1);
+  for (int c = lane; c < nchunk; c += 32) {
+    const ChunkGeom g = chunk_geom(o, c);
+    const int k = kbase + g.k;
+    int cnt;
+    if (!o.mn) { cnt = K - k; cnt = g.rows4 ? (cnt > 4 ? 4 : cnt) : 0; }
+    else cnt = k < K ? g.rows4 : 0;
+    const int one = k < K ? g.one : -1;
+    const uint32_t dst = sbase + g.dst;
+    const float *src = o.base + g.src + kstep;
+    if (cnt == 4 && o.fast) cp_async16(dst, src);
+    else if (cnt <= 0 && one < 0) st_shared_zero16(dst);
+    else {
 #pragma unroll
-        for (int e = 0; e < 4; e++) {
-          if (e < cnt) cp_async4(dst + 4 * e, src + e);
-          else st_shared_f32(dst + 4 * e, e == one ? 1.f : 0.f);
-        }
+      for (int e = 0; e < 4; e++) {
+        if (e < cnt) cp_async4(dst + 4 * e, src + e);
+        else st_shared_f32(dst + 4 * e, e == one ? 1.f : 0.f);
       }
     }
   }
 }
 
+/* The common case -- every row of the tile inside the matrix, 16-byte aligned, the k-block entirely below K -- with the chunk
+ * walk reduced to pointer increments (same chunk -> lane assignment as chunk_geom: chunk = lane + 32 i). */
+__device__ __forceinline__ bool tile_interior(const Operand &o) {
+  const int padded = o.mn ? ((o.tile_rows + 31) & ~31) : o.tile_rows;
+  return o.fast && o.row0 + padded <= o.rows;
+}
+__device__ __forceinline__ void load_tile_interior(const Operand &o, uint32_t sbase, int kb, int lane) {
+  const int kbase = kb * RR_TC_BK;
+  if (!o.mn) {
+    const int l = lane & 7, kq = lane >> 3;
+    const float *src = o.base + (size_t)(o.row0 + l) * o.ld + kbase + kq * 4;
+    uint32_t dst = sbase + kq * 128 + l * 16;
+    const size_t step = (size_t)8 * o.ld;
+#pragma unroll 4
+    for (int g = 0; g < o.tile_rows / 8; g++) {
+      cp_async16(dst, src);
+      cp_async16(dst + 512, src + 16);
+      src += step;
+      dst += 1024;
+    }
+  } else {
+    const int j = lane & 7, kr = lane >> 3;
+    const float *src0 = o.base + (size_t)(kbase + kr) * o.ld + o.row0 + j * 4;
+    uint32_t dst = sbase + kr * 128 + ((((j >> 1) ^ kr) << 5) | ((j & 1) << 4));
+    const size_t step = (size_t)4 * o.ld;
+    for (int mb = 0; mb < (o.tile_rows + 31) / 32; mb++) {
+      const float *src = src0 + mb * 32;
+#pragma unroll
+      for (int kq = 0; kq < 8; kq++) {
+        cp_async16(dst, src);
+        src += step;
+        dst += 512;
+      }
+    }
+  }
+}
+__device__ __forceinline__ void load_stage(const Operand &o, bool interior, uint32_t sbase, int kb, int K, int lane) {
+  if (interior && (kb + 1) * RR_TC_BK <= K) load_tile_interior(o, sbase, kb, lane);
+  else load_tile(o, sbase, kb, K, lane);
+}
+
+/* sigmoid with the fast exponential and reciprocal (relative error ~1e-6, far below TF32) */
+__device__ __forceinline__ float sigmoid_fast(float z) { return __fdividef(1.f, 1.f + __expf(-z)); }
+
 __global__ void __launch_bounds__(RR_TC_THREADS) gemm_kernel(const rr_tc_problem *__restrict__ probs, int nprob) {
   extern __shared__ __align__(1024) uint8_t tc_smem[];
-  __shared__ __align__(8) uint64_t bars[RR_TC_STAGES];
+  __shared__ __align__(8) uint64_t full_bar[RR_TC_STAGES], empty_bar[RR_TC_STAGES], done_bar;
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -184,7 +246,11 @@ __global__ void __launch_bounds__(RR_TC_THREADS) gemm_kernel(const rr_tc_problem
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tid == 0) {
-    for (int s = 0; s < RR_TC_STAGES; s++) mbar_init(smem_u32(&bars[s]), 1);
+    for (int s = 0; s < RR_TC_STAGES; s++) {
+      mbar_init(smem_u32(&full_bar[s]), 32); /* the 32 lanes of the stage's producer warp */
+      mbar_init(smem_u32(&empty_bar[s]), 1); /* tcgen05.commit */
+    }
+    mbar_init(smem_u32(&done_bar), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -199,19 +265,38 @@ __global__ void __launch_bounds__(RR_TC_THREADS) gemm_kernel(const rr_tc_problem
   const uint32_t a_lbo = p.a_mn ? 4096 : 128, a_sbo = p.a_mn ? 512 : 1024, a_step = p.a_mn ? 1024 : 256, a_type = p.a_mn ? 1 : 0;
   const uint32_t b_lbo = p.b_mn ? 4096 : 128, b_sbo = p.b_mn ? 512 : 1024, b_step = p.b_mn ? 1024 : 256, b_type = p.b_mn ? 1 : 0;
 
-  for (int s = 0; s < RR_TC_STAGES - 1; s++) {
-    if (s < nkb) {
-      load_tile(oa, smem0 + s * stage_bytes, s, K, tid);
-      load_tile(ob, smem0 + s * stage_bytes + a_bytes, s, K, tid);
+  /* optional per-CTA cycle counters (tools/tc_learner_timing.py --prof): reserved[0..1] = address of int64 [tiles][8] */
+  long long *prof = reinterpret_cast<long long *>(((unsigned long long)(uint32_t)p.reserved[1] << 32) | (uint32_t)p.reserved[0]);
+  if (prof) prof += (size_t)blockIdx.x * 8;
+  const long long t_start = prof ? clock64() : 0;
+  if (warp < RR_TC_STAGES) {
+    /* producer warp w owns stage w: k-blocks w, w + STAGES, ...  Waiting for its own copies (wait_group 0) and the proxy
+     * fence then only ever see this stage's traffic; the other stages' copies stay in flight in the other producer warps
+     * (with all warps loading all stages, fence.proxy.async drained the whole ring every k-block: 2 us per k-block). */
+    const int s = warp;
+    const bool int_a = tile_interior(oa), int_b = tile_interior(ob);
+    const uint32_t sa = smem0 + s * stage_bytes, sb = sa + a_bytes;
+    for (int kb = warp, use = 0; kb < nkb; kb += RR_TC_STAGES, use++) {
+      const long long t0 = prof ? clock64() : 0;
+      if (use >= 1) mbar_wait(smem_u32(&empty_bar[s]), (uint32_t)((use - 1) & 1));
+      const long long t1 = prof ? clock64() : 0;
+      load_stage(oa, int_a, sa, kb, K, lane);
+      load_stage(ob, int_b, sb, kb, K, lane);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      const long long t2 = prof ? clock64() : 0;
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      const long long t3 = prof ? clock64() : 0;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      if (prof && tid == 0) { prof[0] += t1 - t0; prof[1] += t2 - t1; prof[2] += t3 - t2; prof[3] += clock64() - t3; }
+      asm volatile("{\n\t.reg .b64 state;\n\tmbarrier.arrive.shared::cta.b64 state, [%0];\n\t}" ::"r"(smem_u32(&full_bar[s])) : "memory");
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  }
-  for (int kb = 0; kb < nkb; kb++) {
-    const int s = kb % RR_TC_STAGES;
-    asm volatile("cp.async.wait_group %0;" ::"n"(RR_TC_STAGES - 2) : "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncthreads();
-    if (tid == 0) {
+  } else if (tid == RR_TC_STAGES * 32) {
+    /* MMA issuer: one thread */
+    for (int kb = 0; kb < nkb; kb++) {
+      const int s = kb % RR_TC_STAGES;
+      const long long t0 = prof ? clock64() : 0;
+      mbar_wait(smem_u32(&full_bar[s]), (uint32_t)((kb / RR_TC_STAGES) & 1));
+      if (prof) prof[4] += clock64() - t0;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t sa = smem0 + s * stage_bytes, sb = sa + a_bytes;
 #pragma unroll
@@ -225,28 +310,27 @@ __global__ void __launch_bounds__(RR_TC_THREADS) gemm_kernel(const rr_tc_problem
             ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
             : "memory");
       }
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bars[s])) : "memory");
+      /* frees the stage for its producer once these MMAs have read it */
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&empty_bar[s])) : "memory");
     }
-    const int nxt = kb + RR_TC_STAGES - 1;
-    if (nxt < nkb) {
-      const int sn = nxt % RR_TC_STAGES; /* == (kb - 1) % STAGES: free once the MMAs of k-block kb - 1 have read it */
-      if (kb >= 1) mbar_wait(smem_u32(&bars[sn]), (uint32_t)(((kb - 1) / RR_TC_STAGES) & 1));
-      load_tile(oa, smem0 + sn * stage_bytes, nxt, K, tid);
-      load_tile(ob, smem0 + sn * stage_bytes + a_bytes, nxt, K, tid);
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&done_bar)) : "memory");
   }
-  /* the last commit covers every MMA issued before it */
-  mbar_wait(smem_u32(&bars[(nkb - 1) % RR_TC_STAGES]), (uint32_t)(((nkb - 1) / RR_TC_STAGES) & 1));
+  __syncwarp();
+  const long long t_loop = prof ? clock64() : 0;
+  mbar_wait(smem_u32(&done_bar), 0); /* every MMA has written its accumulator */
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const long long t_done = prof ? clock64() : 0;
 
-  const int row = tile_m * RR_TC_BM + warp * 32 + lane;
+  /* warp w reads TMEM lanes 32 (w % 4) .. + 31 (the hardware's lane window of a warp); warps 0-3 take the even 16-column
+   * groups, warps 4-7 the odd ones */
+  const int lane_q = warp & 3;
+  const int row = tile_m * RR_TC_BM + lane_q * 32 + lane;
   const bool vec_d = (p.ldd % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.d) & 15) == 0);
   const float *auxp = p.epi == 1 ? p.aux_out : (p.epi == 2 ? p.aux_in : nullptr);
   const bool vec_aux = !auxp || ((p.ldaux % 4 == 0) && ((reinterpret_cast<uintptr_t>(auxp) & 15) == 0));
-  for (int j = 0; j < BN / 16; j++) {
+  for (int j = warp >> 2; j < BN / 16; j += RR_TC_THREADS / 128) {
     uint32_t v[16];
-    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(j * 16);
+    const uint32_t taddr = tmem + ((uint32_t)(lane_q * 32) << 16) + (uint32_t)(j * 16);
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
@@ -276,7 +360,7 @@ __global__ void __launch_bounds__(RR_TC_THREADS) gemm_kernel(const rr_tc_problem
           for (int i = 0; i < 4; i++) ap[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
         }
 #pragma unroll
-        for (int i = 0; i < 16; i++) o[i] *= rr_tc_sigmoid(o[i]);
+        for (int i = 0; i < 16; i++) o[i] = round_tf32(o[i] * sigmoid_fast(o[i]));
       } else if (p.epi == 2) {
         const float4 *ap = reinterpret_cast<const float4 *>(p.aux_in + (size_t)row * p.ldaux + c0);
 #pragma unroll
@@ -286,8 +370,8 @@ __global__ void __launch_bounds__(RR_TC_THREADS) gemm_kernel(const rr_tc_problem
         }
 #pragma unroll
         for (int i = 0; i < 16; i++) {
-          const float sg = rr_tc_sigmoid(z[i]);
-          o[i] *= sg * (1.f + z[i] * (1.f - sg));
+          const float sg = sigmoid_fast(z[i]);
+          o[i] = round_tf32(o[i] * sg * (1.f + z[i] * (1.f - sg)));
         }
       }
       float4 *dst = reinterpret_cast<float4 *>(p.d + (size_t)row * p.ldd + c0);
@@ -302,6 +386,7 @@ __global__ void __launch_bounds__(RR_TC_THREADS) gemm_kernel(const rr_tc_problem
       }
     }
   }
+  if (prof && tid == RR_TC_STAGES * 32) { prof[5] = t_done - t_loop; prof[6] = t_done - t_start; prof[7] = clock64() - t_done; }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(ncols) : "memory");

@@ -419,6 +419,10 @@ class PPO:
         """lax.pmean(grads): one flat fp32 bucket (2.53 MB for the rodent networks) per minibatch over NCCL."""
         if self.world == 1:
             return
+        if self._use_tc and self._tc is not None:   # the gradients already live in one flat buffer
+            dist.all_reduce(self._tc.flat_grad)
+            self._tc.flat_grad.div_(self.world)
+            return
         grads = [p.grad for p in self.params]
         if self._flat_grad is None:
             self._flat_grad = torch.empty(sum(g.numel() for g in grads), device=self.device)

@@ -40,7 +40,8 @@ def problem(a: torch.Tensor, b: torch.Tensor, d: torch.Tensor, *, a_t: bool = Fa
 
 
 class TcGroup:
-    def __init__(self, L, problems: List[Dict], device):
+    def __init__(self, L, problems: List[Dict], device, prof: Optional[torch.Tensor] = None):
+        """`prof`: int64 [>= tiles, 8] device tensor for the kernel's per-CTA cycle counters (tools/tc_learner_timing.py)."""
         self.L, self.n, self.device = L, len(problems), torch.device(device)
         self._keep = problems  # the tensors whose addresses are baked into the descriptors
         arr = (_lib.RRTcProblem * self.n)()
@@ -52,6 +53,9 @@ class TcGroup:
                 setattr(q, name, t.data_ptr() if t is not None else None)
             for name in ("m", "n", "k", "lda", "ldb", "ldd", "ldaux", "a_mn", "b_mn", "epi", "b_ones"):
                 setattr(q, name, int(p[name]))
+            if prof is not None:
+                addr = prof.data_ptr()
+                q.reserved[0], q.reserved[1] = ctypes.c_int32(addr & 0xFFFFFFFF).value, ctypes.c_int32(addr >> 32).value
         tiles, smem = ctypes.c_int32(), ctypes.c_int32()
         _lib.check(L, L.rr_tc_plan(arr, self.n, ctypes.byref(tiles), ctypes.byref(smem)))
         self.tiles, self.smem = tiles.value, smem.value

@@ -6,8 +6,9 @@ brax_rodent_run_ppo.py:97-114, 200) by 12 grouped launches:
                bias + SiLU fused, the pre-activations kept for the backward pass
   loss      2: rr_ppo_loss (d loss / d logits, d loss / d baseline)
   dgrad     5: dZ_{l-1} = (dZ_l W_l) * silu'(Z_{l-1}) for both nets per launch (W read MN-major: no transposed copy)
-  wgrad     1: all eleven dW_l = dZ_l' X_l in one launch, db_l as the product's extra "ones" column, written straight into the
-               parameters' .grad tensors
+  wgrad     1: all eleven dW_l = dZ_l' X_l in one launch (each split four ways over the rows; the partial sums are added in a fixed
+               order by one torch.sum), db_l as the product's extra "ones" column; the parameters' .grad tensors are views of one
+               flat buffer, which is also the NCCL all-reduce bucket
 The parameters stay ordinary nn.Linear weights (acting, export and the optimizer are unchanged).
 """
 from __future__ import annotations
@@ -45,9 +46,19 @@ class TcLearner:
         self.logits, self.grad_logits = new(M, self.lp[-1].out_features), new(M, self.lp[-1].out_features)
         self.baseline, self.grad_baseline = new(M, 1), new(M, 1)
         self.bootstrap = new(Mb, 1)
-        for lin in self.lp + self.lv:  # static gradient tensors: the wgrad launch overwrites them completely
-            lin.weight.grad = torch.zeros_like(lin.weight)
-            lin.bias.grad = torch.zeros_like(lin.bias)
+        # static gradient tensors: views of ONE flat buffer (16-byte aligned pieces), which is also the all-reduce bucket
+        sizes = [((p.numel() + 3) // 4) * 4 for lin in self.lp + self.lv for p in (lin.weight, lin.bias)]
+        self.flat_grad = torch.zeros(sum(sizes), device=dev)
+        self._grad_off, off = {}, 0
+        for lin in self.lp + self.lv:
+            for p in (lin.weight, lin.bias):
+                self._grad_off[id(p)] = off
+                p.grad = self.flat_grad[off:off + p.numel()].view_as(p)
+                off += ((p.numel() + 3) // 4) * 4
+        # the weight gradients reduce over all M rows: split them over `splits` CTAs per output tile (partial sums in a
+        # workspace with the flat buffer's layout, summed in a fixed order afterwards -> deterministic)
+        self.splits = 4 if (M % 4 == 0 and M // 4 >= 256) else 1
+        self.ws = torch.zeros(self.splits, self.flat_grad.numel(), device=dev) if self.splits > 1 else None
 
         def fwd(lins, l, inp, h, z, out):
             lin, last = lins[l], l == len(lins) - 1
@@ -86,13 +97,21 @@ class TcLearner:
                 probs.append(cv[iv])
             self.dgrad_groups.append(TcGroup(L, probs, dev))
 
-        def wgrad(lins, dz, h, g_head, l):
+        def wgrad(lins, dz, h, g_head, l, sp):
             dz_l = g_head if l == len(lins) - 1 else dz[l]
             inp = self.x if l == 0 else h[l - 1]
-            return problem(dz_l, inp, lins[l].weight.grad, a_t=True, b_t=True, ones_out=lins[l].bias.grad)
+            w, b = lins[l].weight, lins[l].bias
+            if self.splits == 1:
+                return problem(dz_l, inp, w.grad, a_t=True, b_t=True, ones_out=b.grad)
+            rows = slice(sp * (M // self.splits), (sp + 1) * (M // self.splits))
+            ow, ob = self._grad_off[id(w)], self._grad_off[id(b)]
+            return problem(dz_l[rows], inp[rows], self.ws[sp, ow:ow + w.numel()].view_as(w), a_t=True, b_t=True,
+                           ones_out=self.ws[sp, ob:ob + b.numel()])
 
-        probs = [wgrad(self.lv, self.dzv, self.hv, self.grad_baseline, l) for l in range(len(self.lv))]
-        probs += [wgrad(self.lp, self.dzp, self.hp, self.grad_logits, l) for l in range(len(self.lp))]
+        probs = []
+        for sp in range(self.splits):
+            probs += [wgrad(self.lv, self.dzv, self.hv, self.grad_baseline, l, sp) for l in range(len(self.lv))]
+            probs += [wgrad(self.lp, self.dzp, self.hp, self.grad_logits, l, sp) for l in range(len(self.lp))]
         self.wgrad_group = TcGroup(L, probs, dev)
         self.launches_per_update = len(self.fwd_groups) + len(self.dgrad_groups) + 1
 
@@ -106,3 +125,5 @@ class TcLearner:
         for g in self.dgrad_groups:
             g.launch()
         self.wgrad_group.launch()
+        if self.splits > 1:
+            torch.sum(self.ws, dim=0, out=self.flat_grad)

@@ -383,6 +383,14 @@ def test_tc_learner_matches_autograd_on_emulator(emu_lib):
     agent, mb = _loss_case(tiny_env(emu_lib), "cpu", seed=3, T=3, B=5)
     _compare_tc_with_autograd(agent, mb, 2e-4)
     assert agent._tc.launches_per_update == 3 + 2 + 1    # TINY: 3 forward layers, 2 dgrad steps, one wgrad launch
+    assert agent._tc.splits == 1
+
+
+def test_tc_learner_split_wgrad_on_emulator(emu_lib):
+    """Enough rows for the weight gradients to be split four ways over the rows (partials + fixed-order sum)."""
+    agent, mb = _loss_case(tiny_env(emu_lib), "cpu", seed=4, T=4, B=256)
+    _compare_tc_with_autograd(agent, mb, 5e-4)
+    assert agent._tc.splits == 4
 
 
 def test_training_step_with_tc_learner_on_emulator(emu_lib):
@@ -401,8 +409,9 @@ def test_training_step_with_tc_learner_on_emulator(emu_lib):
 
 @pytest.mark.gpu
 def test_tc_learner_matches_autograd_on_gpu():
-    """README minibatch shape (10 x 512 rows, 1264 features, 256-wide value net) through the tcgen05 kernel; both sides use TF32
-    products, so the comparison is at TF32 accuracy."""
+    """README minibatch shape (10 x 512 rows, 1264 features, 256-wide value net) through the tcgen05 kernel against fp32 autograd:
+    TF32 products (10-bit mantissa, the weights truncated by the tensor core) through five layers forward and back, on a case
+    built to have saturated ratios and gradients of 1e8 -- 3 % of each tensor's largest gradient."""
     from brax_rodent_run_b200.env import Rodent
     from brax_rodent_run_b200.ppo import PPO, PPOConfig
     env = Rodent(synthetic_track(), num_envs=2, device="cuda:0", model=load_asset("rodent_0"), iterations=1, ls_iterations=1, n_frames=1)
@@ -410,7 +419,7 @@ def test_tc_learner_matches_autograd_on_gpu():
     agent = PPO(env, cfg)
     _, mb = _loss_case(env, "cuda:0", seed=2, T=10, B=512)
     agent._batch_is_normalized = True
-    _compare_tc_with_autograd(agent, mb, 1e-2)
+    _compare_tc_with_autograd(agent, mb, 3e-2)
 
 
 @pytest.mark.gpu
@@ -460,7 +469,7 @@ def test_graphed_tc_update_matches_eager_autograd_update():
     agent._use_tc = True
     d_eager = torch.cat([(p.detach() - v).reshape(-1) for p, v in zip(agent.params, saved)]).cpu()
     for k in m:
-        assert abs(m_graph[k] - float(m[k])) <= 2e-3 * max(1.0, abs(float(m[k]))), (k, m_graph[k], float(m[k]))
+        assert abs(m_graph[k] - float(m[k])) <= 1e-2 * max(1.0, abs(float(m[k]))), (k, m_graph[k], float(m[k]))
     assert float(d_eager.abs().max()) > 0.1 * cfg.learning_rate
     # Adam's normalised step amplifies relative gradient error where the gradient is tiny: compare in the mean
     assert float((d_graph - d_eager).abs().mean()) < 0.05 * float(d_eager.abs().mean())
