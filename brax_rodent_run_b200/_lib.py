@@ -101,7 +101,8 @@ def load(path: Optional[str] = None):
     L.rr_measure_fp32_peak.argtypes = [ctypes.POINTER(ctypes.c_double), vp]
     L.rr_measure_fp32_peak.restype = ctypes.c_int
     L.rr_launch_count.restype = ctypes.c_longlong
-    L.rr_tc_plan.argtypes = [ctypes.POINTER(RRTcProblem), ctypes.c_int32, c_i, c_i]
+    L.rr_tc_record_bytes.restype = ctypes.c_int32
+    L.rr_tc_plan.argtypes = [ctypes.POINTER(RRTcProblem), ctypes.c_int32, c_i, c_i, vp]
     L.rr_tc_plan.restype = ctypes.c_int
     L.rr_tc_launch.argtypes = [vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, vp]
     L.rr_tc_launch.restype = ctypes.c_int

@@ -7,9 +7,11 @@
  * shared memory holding the whole per-environment working set of a physics substep (about 33 KB for
  * rodent_0.xml), so HBM is touched only to load the 1 KB state + action and to store state + observation.
  */
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <math_constants.h>
 #include <atomic>
 
@@ -282,7 +284,53 @@ static int rrb_launch_ppo_loss(const RRPpoLossArgs &a, void *stream) {
 #include "rr_tc_gemm.h"
 #define RR_TC_BN_MAX 128
 static int rrb_tc_smem_max() { return RR_TC_STAGES * (RR_TC_BM + RR_TC_BN_MAX) * RR_TC_BK * 4; }
-static int rrb_tc_launch(const rr_tc_problem *dev_probs, int count, int total_tiles, int smem_bytes, void *stream) {
+/* Tensor maps for the operands TMA can fetch: 16-byte aligned base and pitch.  cuTensorMapEncodeTiled comes from the driver
+ * through the runtime's entry-point query (the library does not link libcuda); without it every operand takes the cp.async path. */
+typedef CUresult (*rr_encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                       const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                       CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static rr_encode_tiled_fn rrb_encode_fn() {
+  static std::atomic<void *> cached{nullptr};
+  static std::atomic<bool> tried{false};
+  if (!tried.load(std::memory_order_acquire)) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      fn = nullptr;
+    cudaGetLastError();
+    cached.store(fn, std::memory_order_release);
+    tried.store(true, std::memory_order_release);
+  }
+  return (rr_encode_tiled_fn)cached.load(std::memory_order_acquire);
+}
+/* operand stored row-major with pitch ld: K-major = [rows, k] (box 32 k x tile rows, 128-byte swizzle); MN-major = [k, rows]
+ * (box 32 rows x 32 k, 128-byte swizzle with 32-byte atoms) */
+static bool rrb_tc_encode_operand(uint64_t *out, const float *base, int rows, int k, int ld, int mn, int tile_rows) {
+  rr_encode_tiled_fn fn = rrb_encode_fn();
+  if (!fn || (reinterpret_cast<uintptr_t>(base) & 15) || (ld % 4) != 0 || tile_rows > 256) return false;
+  alignas(64) CUtensorMap map;
+  const cuuint64_t dims[2] = {(cuuint64_t)(mn ? rows : k), (cuuint64_t)(mn ? k : rows)};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  const cuuint32_t box[2] = {32, (cuuint32_t)(mn ? 32 : tile_rows)};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, mn ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return false;
+  memcpy(out, &map, sizeof(map));
+  return true;
+}
+static void rrb_tc_encode(RRTcRecord &rec) {
+  static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap size");
+  rr_tc_problem &p = rec.p;
+  int flags = 0;
+  if (getenv("RR_TC_NO_TMA") == nullptr) {
+    if (rrb_tc_encode_operand(rec.tmap_a, p.a, p.m, p.k, p.lda, p.a_mn, RR_TC_BM)) flags |= 1;
+    if (rrb_tc_encode_operand(rec.tmap_b, p.b, p.n, p.k, p.ldb, p.b_mn, p.bn)) flags |= 2;
+  }
+  p.reserved[2] = flags;
+}
+static int rrb_tc_launch(const RRTcRecord *dev_recs, int count, int total_tiles, int smem_bytes, void *stream) {
   static std::atomic<bool> configured[64];
   int dev = 0;
   if (rrb_check(cudaGetDevice(&dev), "cudaGetDevice")) return 1;
@@ -293,7 +341,7 @@ static int rrb_tc_launch(const rr_tc_problem *dev_probs, int count, int total_ti
       return 1;
     configured[dev].store(true, std::memory_order_release);
   }
-  rr_tc::gemm_kernel<<<total_tiles, RR_TC_THREADS, smem_bytes, (cudaStream_t)stream>>>(dev_probs, count);
+  rr_tc::gemm_kernel<<<total_tiles, RR_TC_THREADS, smem_bytes, (cudaStream_t)stream>>>(dev_recs, count);
   return rrb_check(cudaGetLastError(), "rr_tc gemm_kernel launch");
 }
 

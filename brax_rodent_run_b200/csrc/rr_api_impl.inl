@@ -358,9 +358,11 @@ extern "C" int rr_ppo_loss(const rr_ppo_loss_args *u, void *stream) {
 }
 
 /* ---- grouped tensor-core GEMM of the learner ------------------------------------------------------------------ */
-extern "C" int rr_tc_plan(rr_tc_problem *pr, int32_t count, int32_t *total_tiles, int32_t *smem_bytes) {
-  if (!pr || count < 1 || count > 64 || !total_tiles || !smem_bytes) return rr_fail(RR_EINVAL, "rr_tc_plan: bad argument");
-  int tiles = 0, bn_max = 16;
+extern "C" int32_t rr_tc_record_bytes(void) { return (int32_t)sizeof(RRTcRecord); }
+
+extern "C" int rr_tc_plan(rr_tc_problem *pr, int32_t count, int32_t *total_tiles, int32_t *smem_bytes, void *records) {
+  if (!pr || count < 1 || count > 64 || !total_tiles || !smem_bytes || !records) return rr_fail(RR_EINVAL, "rr_tc_plan: bad argument");
+  int tiles = 0;
   for (int i = 0; i < count; i++) {
     rr_tc_problem &p = pr[i];
     if (p.m < 1 || p.n < 1 || p.k < 1 || !p.a || !p.b || !p.d) return rr_fail(RR_EINVAL, "rr_tc_plan: empty problem or null matrix");
@@ -370,25 +372,43 @@ extern "C" int rr_tc_plan(rr_tc_problem *pr, int32_t count, int32_t *total_tiles
         ((p.epi == 2 || (p.epi == 1 && p.aux_out)) && p.ldaux < p.n))
       return rr_fail(RR_EINVAL, "rr_tc_plan: leading dimension smaller than the row length");
     const int n_ext = p.n + (p.b_ones ? 1 : 0), tiles_m = (p.m + 127) / 128;
-    /* narrow tiles (64) keep more SMs busy when there are few row tiles; 128 otherwise */
-    int cap = (tiles_m * ((n_ext + 63) / 64) <= 2 * 148) ? 64 : 128;
+    /* 128-wide tiles halve the A traffic and the tensor core's shared-memory reads per flop; narrower only when n is */
     int bn = (n_ext + 15) / 16 * 16;
-    if (bn > cap) bn = cap;
+    if (bn > 128) bn = 128;
     p.bn = bn;
     p.tiles_n = (n_ext + bn - 1) / bn;
     p.tile_start = tiles;
     tiles += tiles_m * p.tiles_n;
-    if (bn > bn_max) bn_max = bn;
   }
   *total_tiles = tiles;
-  *smem_bytes = 4 * (128 * 128 + (bn_max + 31) / 32 * 4096); /* RR_TC_STAGES x (A tile + B tile) of one 32-wide k-block */
+  /* shared memory of the launch: the largest ring; a problem's ring is 4 stages (3 for the 128-wide tile: two CTAs per SM) of
+   * one 32-wide k-block of A (16 KB) and B */
+  int smem = 0;
+  for (int i = 0; i < count; i++) {
+    rr_tc_problem &p = pr[i];
+    const int stage = 128 * 128 + (p.b_mn ? (p.bn + 31) / 32 * 4096 : p.bn * 128);
+    const int nst = p.bn > 64 ? 3 : 4;
+    p.reserved[3] = nst;
+    if (nst * stage > smem) smem = nst * stage;
+  }
+  *smem_bytes = smem;
   if (*smem_bytes > rrb_tc_smem_max()) return rr_fail(RR_EINVAL, "rr_tc_plan: tile does not fit shared memory");
+  /* device records: the planned problem + the tensor maps of the operands TMA can fetch (backend-specific; none on the emulator) */
+  for (int i = 0; i < count; i++) {
+    RRTcRecord rec;
+    memset(&rec, 0, sizeof(rec));
+    pr[i].reserved[2] = 0;
+    rec.p = pr[i];
+    rrb_tc_encode(rec);
+    pr[i].reserved[2] = rec.p.reserved[2];
+    memcpy((char *)records + (size_t)i * sizeof(RRTcRecord), &rec, sizeof(rec));
+  }
   return RR_OK;
 }
 
-extern "C" int rr_tc_launch(const rr_tc_problem *dev_problems, int32_t count, int32_t total_tiles, int32_t smem_bytes, void *stream) {
+extern "C" int rr_tc_launch(const void *dev_problems, int32_t count, int32_t total_tiles, int32_t smem_bytes, void *stream) {
   if (!dev_problems || count < 1 || total_tiles < 1 || smem_bytes < 1) return rr_fail(RR_EINVAL, "rr_tc_launch: bad argument");
-  if (rrb_tc_launch(dev_problems, count, total_tiles, smem_bytes, stream)) return rr_fail(RR_ECUDA, rrb_error());
+  if (rrb_tc_launch((const RRTcRecord *)dev_problems, count, total_tiles, smem_bytes, stream)) return rr_fail(RR_ECUDA, rrb_error());
   g_rr_launches += 1;
   return RR_OK;
 }

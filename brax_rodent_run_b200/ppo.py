@@ -249,13 +249,15 @@ class PPO:
                                     fused=True if cuda else None)  # one multi-tensor kernel instead of ~15 foreach launches
         self._use_rollout_graph = bool(cfg.rollout_graph) and self.device.type == "cuda"
         self._rg = None             # captured unroll (policy + sample + env step) x unroll_length
-        self._graph = None          # (fwd + bwd [+ Adam]) graph, static minibatch buffers, static metrics
+        self._graph = None          # (gather + fwd + bwd [+ Adam]) graph, static batch / minibatch buffers, static metrics
+        self._static = None
         self._graph_warm = 0
         self.normalizer = RunningStats(obs, self.device)
         self.gen = torch.Generator(device=self.device)
         self.gen.manual_seed(cfg.seed * 1000 + 17 + self.rank)
         self.env_steps = 0
         self._flat_grad = None
+        self._batch_static = None
         # tensor-core learner (tc_learner.py): built at the first loss_and_grads() call, when the minibatch shape is known
         assert not cfg.tc_learner or cfg.fused_loss, "tc_learner needs fused_loss"
         self._use_tc = bool(cfg.tc_learner)
@@ -441,7 +443,7 @@ class PPO:
         all-reduce of the flat gradient bucket and Adam are captured in the same graph (cfg.graph_allreduce; off: the graph
         ends after backward and they run eagerly)."""
         cfg = self.cfg
-        if self._graph is None:
+        if self._graph is None and self._static is None:
             self._static = {k: torch.empty((v.shape[0], cfg.batch_size) + tuple(v.shape[2:]) if k != "next_observation_last"
                                            else (cfg.batch_size,) + tuple(v.shape[1:]), device=self.device, dtype=v.dtype)
                             for k, v in data.items()}
@@ -452,15 +454,27 @@ class PPO:
                 self._tc = TcLearner(self.env._L, self.policy, self.value, T * b, b, self.device)
                 self._static["observation"] = self._tc.x.view(T, b, -1)
                 self._static["next_observation_last"] = self._tc.xb
-        st = self._static
+            # the batch the minibatches are gathered from and the minibatch's indices are static too, so that the gathers are
+            # part of the graph (seven index_select launches per update were most of the host time of an update)
+            self._batch_static = dict(data)  # adopt this batch's tensors; later batches are assembled in them (training_step)
+            self._idx_static = torch.zeros(cfg.batch_size, dtype=idx.dtype, device=self.device)
+        st, batch = self._static, self._batch_static
         for k, v in data.items():
-            torch.index_select(v, 1 if k != "next_observation_last" else 0, idx, out=st[k])
+            if v.data_ptr() != batch[k].data_ptr():
+                batch[k].copy_(v)
+        self._idx_static.copy_(idx)
         st["entropy_noise"].normal_(generator=self.gen)
+
+        def gather():
+            for k, v in batch.items():
+                torch.index_select(v, 1 if k != "next_observation_last" else 0, self._idx_static, out=st[k])
+
         if self._graph is None and self._graph_warm < 3:
             # eager warm-up updates on a side stream (allocator / cuBLAS workspaces / Adam state), as torch's capture recipe
             side = torch.cuda.Stream(self.device)
             side.wait_stream(torch.cuda.current_stream(self.device))
             with torch.cuda.stream(side):
+                gather()
                 metrics = self.loss_and_grads(st, zero_grad_to_none=True)
                 self._allreduce_grads()
                 self.opt.step()
@@ -473,6 +487,7 @@ class PPO:
                 self.opt.zero_grad(set_to_none=True)
             in_graph = self.world == 1 or self.cfg.graph_allreduce
             with torch.cuda.graph(g):
+                gather()
                 metrics = self.loss_and_grads(st, zero_grad_to_none=True)
                 if in_graph:
                     self._allreduce_grads()  # NCCL all-reduce of the flat bucket, captured with the rest (no-op on one rank)
@@ -492,12 +507,19 @@ class PPO:
             state, data = self.unroll(state)
             chunks.append(data)
         # [T, n_unroll * num_envs, ...]: the "batch" axis that brax shuffles is (unroll, env)
-        data = {k: torch.cat([c[k] for c in chunks], dim=1 if k != "next_observation_last" else 0) for k in chunks[0]}
+        obs_keys = ("observation", "next_observation_last")
+        out = getattr(self, "_batch_out", None)   # the update graph's static batch buffers once it exists
+        data = {k: torch.cat([c[k] for c in chunks], dim=1 if k != "next_observation_last" else 0,
+                             out=out[k] if out is not None and k not in obs_keys else None) for k in chunks[0]}
         if cfg.normalize_observations:
             self.normalizer.update(data["observation"], distributed=self.world > 1)
         # the statistics are fixed for all epochs of this batch: normalise (and pad) it once instead of once per minibatch
-        data["observation"] = self._norm(data["observation"])
-        data["next_observation_last"] = self._norm(data["next_observation_last"])
+        for k in obs_keys:
+            normed = self._norm(data[k])
+            if out is not None:
+                out[k].copy_(normed)
+                normed = out[k]
+            data[k] = normed
         self._batch_is_normalized = True
         nb = data["reward"].shape[1]
         metrics = {}
@@ -514,6 +536,8 @@ class PPO:
                 self.opt.step()
         if self._use_graph:
             metrics = {k: v.clone() for k, v in metrics.items()}
+            if self._batch_static is not None:  # from now on the next batches are assembled in the graph's static buffers
+                self._batch_out = self._batch_static
         self._batch_is_normalized = False
         self.env_steps += n_unroll * cfg.unroll_length * cfg.num_envs * self.world
         return state, metrics

@@ -41,7 +41,7 @@ def problem(a: torch.Tensor, b: torch.Tensor, d: torch.Tensor, *, a_t: bool = Fa
 
 class TcGroup:
     def __init__(self, L, problems: List[Dict], device, prof: Optional[torch.Tensor] = None):
-        """`prof`: int64 [>= tiles, 8] device tensor for the kernel's per-CTA cycle counters (tools/tc_learner_timing.py)."""
+        """`prof`: int64 [>= tiles, 16] device tensor for the kernel's per-CTA cycle counters (tools/tc_learner_timing.py)."""
         self.L, self.n, self.device = L, len(problems), torch.device(device)
         self._keep = problems  # the tensors whose addresses are baked into the descriptors
         arr = (_lib.RRTcProblem * self.n)()
@@ -57,15 +57,20 @@ class TcGroup:
                 addr = prof.data_ptr()
                 q.reserved[0], q.reserved[1] = ctypes.c_int32(addr & 0xFFFFFFFF).value, ctypes.c_int32(addr >> 32).value
         tiles, smem = ctypes.c_int32(), ctypes.c_int32()
-        _lib.check(L, L.rr_tc_plan(arr, self.n, ctypes.byref(tiles), ctypes.byref(smem)))
+        rec_bytes = L.rr_tc_record_bytes()
+        self._records = (ctypes.c_uint8 * (rec_bytes * self.n + 128))()
+        base = (ctypes.addressof(self._records) + 127) // 128 * 128   # records hold 128-byte aligned tensor maps
+        _lib.check(L, L.rr_tc_plan(arr, self.n, ctypes.byref(tiles), ctypes.byref(smem), ctypes.c_void_p(base)))
         self.tiles, self.smem = tiles.value, smem.value
+        self.tma = [(q.reserved[2] & 1, (q.reserved[2] >> 1) & 1) for q in arr]
         self._host = arr
         if self.device.type == "cuda":
-            raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+            raw = torch.frombuffer(bytearray(ctypes.string_at(base, rec_bytes * self.n)), dtype=torch.uint8)
             self._dev = raw.to(self.device)
+            assert self._dev.data_ptr() % 128 == 0
             self._ptr = self._dev.data_ptr()
         else:  # emulator backend: "device" pointers are host pointers
-            self._ptr = ctypes.addressof(arr)
+            self._ptr = base
 
     def launch(self) -> None:
         stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream) if self.device.type == "cuda" else None

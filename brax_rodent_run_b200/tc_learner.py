@@ -97,21 +97,32 @@ class TcLearner:
                 probs.append(cv[iv])
             self.dgrad_groups.append(TcGroup(L, probs, dev))
 
+        self.ones_row = torch.ones(1, M, device=dev)
+
         def wgrad(lins, dz, h, g_head, l, sp):
             dz_l = g_head if l == len(lins) - 1 else dz[l]
             inp = self.x if l == 0 else h[l - 1]
             w, b = lins[l].weight, lins[l].bias
-            if self.splits == 1:
-                return problem(dz_l, inp, w.grad, a_t=True, b_t=True, ones_out=b.grad)
             rows = slice(sp * (M // self.splits), (sp + 1) * (M // self.splits))
-            ow, ob = self._grad_off[id(w)], self._grad_off[id(b)]
-            return problem(dz_l[rows], inp[rows], self.ws[sp, ow:ow + w.numel()].view_as(w), a_t=True, b_t=True,
-                           ones_out=self.ws[sp, ob:ob + b.numel()])
+            if self.splits == 1:
+                dw, db = w.grad, b.grad
+            else:
+                ow, ob = self._grad_off[id(w)], self._grad_off[id(b)]
+                dw, db = self.ws[sp, ow:ow + w.numel()].view_as(w), self.ws[sp, ob:ob + b.numel()]
+            if w.shape[0] == 1:
+                # the value head: dZ is a single column (pitch 4 bytes: no tensor map, slow cp.async path as the 128-row operand).
+                # Transposed instead: dW' [K_in, 1] = X' g with g read as the row vector [1, M], db = g . 1
+                g_row = dz_l.view(1, M)
+                return [problem(inp[rows], g_row[:, rows], dw.view(-1, 1), a_t=True),
+                        problem(g_row[:, rows], self.ones_row[:, rows], db.view(1, 1))]
+            return [problem(dz_l[rows], inp[rows], dw, a_t=True, b_t=True, ones_out=db)]
 
         probs = []
         for sp in range(self.splits):
-            probs += [wgrad(self.lv, self.dzv, self.hv, self.grad_baseline, l, sp) for l in range(len(self.lv))]
-            probs += [wgrad(self.lp, self.dzp, self.hp, self.grad_logits, l, sp) for l in range(len(self.lp))]
+            for l in range(len(self.lv)):
+                probs += wgrad(self.lv, self.dzv, self.hv, self.grad_baseline, l, sp)
+            for l in range(len(self.lp)):
+                probs += wgrad(self.lp, self.dzp, self.hp, self.grad_logits, l, sp)
         self.wgrad_group = TcGroup(L, probs, dev)
         self.launches_per_update = len(self.fwd_groups) + len(self.dgrad_groups) + 1
 

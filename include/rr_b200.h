@@ -154,8 +154,10 @@ int rr_ppo_loss(const rr_ppo_loss_args *args, void *stream);
  *                 2: D = (acc + bias) * silu'(aux_in)         (dgrad through the previous layer's activation)
  *   b_ones        B gets a virtual extra row n of ones (MN-major B only): column n of the product, the sum of A over k --
  *                 the bias gradient when A = dY' -- goes to ones_out[m]
- * rr_tc_plan validates a HOST array and fills bn / tile_start / tiles_n; rr_tc_launch takes a DEVICE copy of the planned array
- * (so that the launch is capturable in a CUDA graph).  All matrices are DEVICE pointers. */
+ * rr_tc_plan validates a HOST array, fills bn / tile_start / tiles_n and writes one device record per problem (the planned problem
+ * + TMA tensor maps of the operands whose base and pitch are 16-byte aligned; the others are fetched with cp.async);
+ * rr_tc_launch takes a DEVICE copy of the records (so that the launch is capturable in a CUDA graph).  All matrices are DEVICE
+ * pointers. */
 typedef struct rr_tc_problem {
   const float *a, *b;
   float *d;
@@ -166,8 +168,10 @@ typedef struct rr_tc_problem {
   int32_t bn, tile_start, tiles_n; /* filled by rr_tc_plan */
   int32_t reserved[4];
 } rr_tc_problem;
-int rr_tc_plan(rr_tc_problem *host_problems, int32_t count, int32_t *total_tiles, int32_t *smem_bytes);
-int rr_tc_launch(const rr_tc_problem *device_problems, int32_t count, int32_t total_tiles, int32_t smem_bytes, void *stream);
+int32_t rr_tc_record_bytes(void);
+int rr_tc_plan(rr_tc_problem *host_problems, int32_t count, int32_t *total_tiles, int32_t *smem_bytes,
+               void *host_records /* count x rr_tc_record_bytes(): copy to the device for rr_tc_launch */);
+int rr_tc_launch(const void *device_records, int32_t count, int32_t total_tiles, int32_t smem_bytes, void *stream);
 
 /* Parity-test hooks: per-environment dump of forward-pass intermediates (tests only). */
 int rr_debug_field(const rr_model *m, const char *name, int32_t *offset, int32_t *count);

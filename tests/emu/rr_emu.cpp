@@ -222,8 +222,9 @@ static int rrb_launch_ppo_loss(const RRPpoLossArgs &a, void *) {
 #define RR_TC_HD static inline
 #include "../../brax_rodent_run_b200/csrc/rr_tc_gemm.h"
 static int rrb_tc_smem_max() { return RR_TC_STAGES * (RR_TC_BM + 128) * RR_TC_BK * 4; }
-static int rrb_tc_launch(const rr_tc_problem *probs, int count, int, int, void *) {
-  for (int i = 0; i < count; i++) rr_tc_reference(probs[i]);
+static void rrb_tc_encode(RRTcRecord &) {} /* no TMA on the host */
+static int rrb_tc_launch(const RRTcRecord *recs, int count, int, int, void *) {
+  for (int i = 0; i < count; i++) rr_tc_reference(recs[i].p);
   return 0;
 }
 

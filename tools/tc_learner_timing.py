@@ -31,9 +31,9 @@ def timeit(fn, n=30):
 
 if "--prof" in sys.argv:  # per-CTA cycle counters of the kernel's pipeline roles
     from brax_rodent_run_b200.tc_gemm import TcGroup
-    names = ["prod0 wait-empty", "prod0 issue", "prod0 wait-landed", "prod0 fence+arrive", "mma wait-full", "drain", "start->done", "epilogue"]
+    names = ["prod0 wait-empty", "prod0 issue", "prod0 wait-landed", "prod0 fence+arrive", "mma wait-full", "drain", "start->done", "epilogue", "mma issue x4", "commit"]
     for name, g in (("fwd0", tc.fwd_groups[0]), ("fwd1", tc.fwd_groups[1]), ("dgrad1", tc.dgrad_groups[1]), ("wgrad", tc.wgrad_group)):
-        prof = torch.zeros(g.tiles, 8, dtype=torch.int64, device="cuda:0")
+        prof = torch.zeros(g.tiles, 16, dtype=torch.int64, device="cuda:0")
         gp = TcGroup(env._L, g._keep, "cuda:0", prof=prof)
         gp.launch(); torch.cuda.synchronize(); prof.zero_()
         gp.launch(); torch.cuda.synchronize()
