@@ -60,6 +60,11 @@ class RRTcProblem(ctypes.Structure):
                 [("reserved", ctypes.c_int32 * 4)])
 
 
+class RRGatherItem(ctypes.Structure):
+    """rr_gather_item (include/rr_b200.h)."""
+    _fields_ = [("src", vp), ("dst", vp)] + [(n, ctypes.c_int32) for n in ("outer", "src_rows", "inner", "reserved")]
+
+
 _libs = {}
 
 
@@ -101,6 +106,10 @@ def load(path: Optional[str] = None):
     L.rr_measure_fp32_peak.argtypes = [ctypes.POINTER(ctypes.c_double), vp]
     L.rr_measure_fp32_peak.restype = ctypes.c_int
     L.rr_launch_count.restype = ctypes.c_longlong
+    L.rr_adam_step.argtypes = [vp, vp, vp, vp, vp, ctypes.c_int64] + [ctypes.c_float] * 4 + [vp]
+    L.rr_adam_step.restype = ctypes.c_int
+    L.rr_gather_rows.argtypes = [ctypes.POINTER(RRGatherItem), ctypes.c_int32, vp, ctypes.c_int32, vp]
+    L.rr_gather_rows.restype = ctypes.c_int
     L.rr_tc_record_bytes.restype = ctypes.c_int32
     L.rr_tc_plan.argtypes = [ctypes.POINTER(RRTcProblem), ctypes.c_int32, c_i, c_i, vp]
     L.rr_tc_plan.restype = ctypes.c_int

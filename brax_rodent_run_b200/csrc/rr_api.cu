@@ -279,6 +279,50 @@ static int rrb_launch_ppo_loss(const RRPpoLossArgs &a, void *stream) {
   return rrb_check(cudaGetLastError(), "rr_ppo_loss launch");
 }
 
+/* ---- Adam on the flat parameter buffer, minibatch gather (rr_learner_misc.h) ---- */
+#define RR_MISC_HD __host__ __device__ static inline
+#include "rr_learner_misc.h"
+__global__ void rr_adam_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v,
+                               const float *__restrict__ step, long long n, float lr, float b1, float b2, float eps) {
+  const float t = step[0] + 1.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float pi = p[i], mi = m[i], vi = v[i];
+    rr_adam_element(pi, g[i], mi, vi, t, lr, b1, b2, eps);
+    p[i] = pi; m[i] = mi; v[i] = vi;
+  }
+}
+__global__ void rr_adam_step_inc_kernel(float *step) { step[0] += 1.f; }
+static int rrb_adam_step(float *p, const float *g, float *m, float *v, float *step, long long n, float lr, float b1, float b2,
+                         float eps, void *stream) {
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  rr_adam_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, step, n, lr, b1, b2, eps);
+  rr_adam_step_inc_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step);
+  return rrb_check(cudaGetLastError(), "rr_adam_kernel launch");
+}
+/* one block per gathered row: dst[t, j, :] = src[t, idx[j], :] */
+__global__ void rr_gather_kernel(const __grid_constant__ RRGatherArgs a) {
+  int it = 0;
+  for (int i = 1; i < a.count; i++)
+    if ((int)blockIdx.x >= a.block_start[i]) it = i;
+  const rr_gather_item g = a.item[it];
+  const int r = blockIdx.x - a.block_start[it], t = r / a.rows, j = r % a.rows;
+  const long long src_row = a.idx[j];
+  const float *src = g.src + ((size_t)t * g.src_rows + src_row) * g.inner;
+  float *dst = g.dst + ((size_t)t * a.rows + j) * g.inner;
+  if ((g.inner & 3) == 0 && ((reinterpret_cast<uintptr_t>(g.src) | reinterpret_cast<uintptr_t>(g.dst)) & 15) == 0) {
+    const float4 *s4 = reinterpret_cast<const float4 *>(src);
+    float4 *d4 = reinterpret_cast<float4 *>(dst);
+    for (int i = threadIdx.x; i < g.inner / 4; i += blockDim.x) d4[i] = s4[i];
+  } else {
+    for (int i = threadIdx.x; i < g.inner; i += blockDim.x) dst[i] = src[i];
+  }
+}
+static int rrb_gather_rows(const RRGatherArgs &a, int blocks, void *stream) {
+  rr_gather_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(a);
+  return rrb_check(cudaGetLastError(), "rr_gather_kernel launch");
+}
+
 /* grouped TF32 GEMM of the learner on the tensor cores (tcgen05) */
 #define RR_TC_HD __host__ __device__ static inline
 #include "rr_tc_gemm.h"

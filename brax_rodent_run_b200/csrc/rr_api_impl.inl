@@ -22,6 +22,7 @@
 #include "../../include/rr_b200.h"
 #include "rr_model_build.h"
 #include "rr_ppo_loss.h"
+#include "rr_learner_misc.h"
 
 static thread_local std::string g_rr_error;
 static std::atomic<long long> g_rr_launches{0};
@@ -409,6 +410,33 @@ extern "C" int rr_tc_plan(rr_tc_problem *pr, int32_t count, int32_t *total_tiles
 extern "C" int rr_tc_launch(const void *dev_problems, int32_t count, int32_t total_tiles, int32_t smem_bytes, void *stream) {
   if (!dev_problems || count < 1 || total_tiles < 1 || smem_bytes < 1) return rr_fail(RR_EINVAL, "rr_tc_launch: bad argument");
   if (rrb_tc_launch((const RRTcRecord *)dev_problems, count, total_tiles, smem_bytes, stream)) return rr_fail(RR_ECUDA, rrb_error());
+  g_rr_launches += 1;
+  return RR_OK;
+}
+
+extern "C" int rr_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, float *step, int64_t n, float lr,
+                            float beta1, float beta2, float eps, void *stream) {
+  if (!param || !grad || !exp_avg || !exp_avg_sq || !step || n < 1) return rr_fail(RR_EINVAL, "rr_adam_step: bad argument");
+  if (rrb_adam_step(param, grad, exp_avg, exp_avg_sq, step, n, lr, beta1, beta2, eps, stream)) return rr_fail(RR_ECUDA, rrb_error());
+  g_rr_launches += 2;
+  return RR_OK;
+}
+
+extern "C" int rr_gather_rows(const rr_gather_item *items, int32_t count, const int64_t *idx, int32_t rows, void *stream) {
+  if (!items || count < 1 || count > RR_GATHER_MAX || !idx || rows < 1) return rr_fail(RR_EINVAL, "rr_gather_rows: bad argument");
+  RRGatherArgs a;
+  memset(&a, 0, sizeof(a));
+  a.count = count; a.rows = rows; a.idx = idx;
+  int blocks = 0;
+  for (int i = 0; i < count; i++) {
+    if (!items[i].src || !items[i].dst || items[i].outer < 1 || items[i].src_rows < 1 || items[i].inner < 1)
+      return rr_fail(RR_EINVAL, "rr_gather_rows: bad item");
+    a.item[i] = items[i];
+    a.block_start[i] = blocks;
+    blocks += items[i].outer * rows;
+  }
+  a.block_start[count] = blocks;
+  if (rrb_gather_rows(a, blocks, stream)) return rr_fail(RR_ECUDA, rrb_error());
   g_rr_launches += 1;
   return RR_OK;
 }

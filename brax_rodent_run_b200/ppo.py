@@ -245,8 +245,18 @@ class PPO:
             torch.backends.cuda.matmul.allow_tf32 = True
             torch.backends.cudnn.allow_tf32 = True
         cuda = self.device.type == "cuda"
-        self.opt = torch.optim.Adam(self.params, lr=cfg.learning_rate, eps=1e-8, capturable=self._use_graph,
-                                    fused=True if cuda else None)  # one multi-tensor kernel instead of ~15 foreach launches
+        # tensor-core learner (tc_learner.py): parameters, gradients and the Adam state live in flat buffers from the start (the
+        # rollout graph captures the parameters' addresses); the GEMM launch lists are built at the first loss_and_grads() call
+        assert not cfg.tc_learner or cfg.fused_loss, "tc_learner needs fused_loss"
+        self._use_tc = bool(cfg.tc_learner)
+        self._tc = None
+        if self._use_tc:
+            from .tc_learner import FlatAdam, flatten_parameters
+            self._flat_param, self._flat_g, self._flat_off = flatten_parameters(self.params, self.device)
+            self.opt = FlatAdam(env._L, self._flat_param, self._flat_g, cfg.learning_rate, eps=1e-8)
+        else:
+            self.opt = torch.optim.Adam(self.params, lr=cfg.learning_rate, eps=1e-8, capturable=self._use_graph,
+                                        fused=True if cuda else None)  # one multi-tensor kernel instead of ~15 foreach launches
         self._use_rollout_graph = bool(cfg.rollout_graph) and self.device.type == "cuda"
         self._rg = None             # captured unroll (policy + sample + env step) x unroll_length
         self._graph = None          # (gather + fwd + bwd [+ Adam]) graph, static batch / minibatch buffers, static metrics
@@ -258,10 +268,7 @@ class PPO:
         self.env_steps = 0
         self._flat_grad = None
         self._batch_static = None
-        # tensor-core learner (tc_learner.py): built at the first loss_and_grads() call, when the minibatch shape is known
-        assert not cfg.tc_learner or cfg.fused_loss, "tc_learner needs fused_loss"
-        self._use_tc = bool(cfg.tc_learner)
-        self._tc = None
+        self._gather_items = None
 
     # ---- acting -----------------------------------------------------------------------------------------------------
     def _norm(self, obs):
@@ -400,7 +407,7 @@ class PPO:
         T, b = obs.shape[0], obs.shape[1]
         if self._tc is None or self._tc.x.shape[0] != T * b:
             from .tc_learner import TcLearner
-            self._tc = TcLearner(self.env._L, self.policy, self.value, T * b, b, self.device)
+            self._tc = TcLearner(self.env._L, self.policy, self.value, T * b, b, self.device, self._flat_g, self._flat_off)
         tc = self._tc
         if obs.data_ptr() != tc.x.data_ptr():
             tc.x.copy_(obs.reshape(T * b, -1))
@@ -451,7 +458,7 @@ class PPO:
             if self._use_tc:  # gather the minibatch straight into the tensor-core learner's input buffers
                 from .tc_learner import TcLearner
                 T, b = data["observation"].shape[0], cfg.batch_size
-                self._tc = TcLearner(self.env._L, self.policy, self.value, T * b, b, self.device)
+                self._tc = TcLearner(self.env._L, self.policy, self.value, T * b, b, self.device, self._flat_g, self._flat_off)
                 self._static["observation"] = self._tc.x.view(T, b, -1)
                 self._static["next_observation_last"] = self._tc.xb
             # the batch the minibatches are gathered from and the minibatch's indices are static too, so that the gathers are
@@ -466,8 +473,21 @@ class PPO:
         st["entropy_noise"].normal_(generator=self.gen)
 
         def gather():
-            for k, v in batch.items():
-                torch.index_select(v, 1 if k != "next_observation_last" else 0, self._idx_static, out=st[k])
+            if self._gather_items is None:  # one launch for all seven tensors (rr_gather_rows)
+                keys = list(batch)
+                assert all(batch[k].dtype == torch.float32 and batch[k].is_contiguous() and st[k].is_contiguous() for k in keys)
+                items = (_lib.RRGatherItem * len(keys))()
+                for it, k in zip(items, keys):
+                    v = batch[k]
+                    lead = 2 if k != "next_observation_last" else 1      # [T, N, ...] or [N, ...]
+                    it.src, it.dst = v.data_ptr(), st[k].data_ptr()
+                    it.outer = v.shape[0] if lead == 2 else 1
+                    it.src_rows = v.shape[lead - 1]
+                    it.inner = int(math.prod(v.shape[lead:]))
+                self._gather_items = items
+            stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            _lib.check(self.env._L, self.env._L.rr_gather_rows(self._gather_items, len(self._gather_items),
+                                                               ctypes.c_void_p(self._idx_static.data_ptr()), cfg.batch_size, stream))
 
         if self._graph is None and self._graph_warm < 3:
             # eager warm-up updates on a side stream (allocator / cuBLAS workspaces / Adam state), as torch's capture recipe

@@ -173,6 +173,21 @@ int rr_tc_plan(rr_tc_problem *host_problems, int32_t count, int32_t *total_tiles
                void *host_records /* count x rr_tc_record_bytes(): copy to the device for rr_tc_launch */);
 int rr_tc_launch(const void *device_records, int32_t count, int32_t total_tiles, int32_t smem_bytes, void *stream);
 
+/* Adam on flat fp32 arrays with torch.optim.Adam's arithmetic (no weight decay, no amsgrad; optax.adam in brax's ppo.train):
+ * `step` is a DEVICE float holding the number of steps taken so far; the call uses step + 1 in the bias corrections and then
+ * stores step + 1 (capturable in a CUDA graph).  All pointers DEVICE. */
+int rr_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, float *step, int64_t n, float lr, float beta1,
+                 float beta2, float eps, void *stream);
+
+/* Minibatch gather of the learner: for every item, dst[t, j, :] = src[t, idx[j], :] (src [outer, src_rows, inner], dst
+ * [outer, rows, inner], fp32, contiguous); one launch for all items (at most 8).  idx: DEVICE int64 [rows]. */
+typedef struct rr_gather_item {
+  const float *src;
+  float *dst;
+  int32_t outer, src_rows, inner, reserved;
+} rr_gather_item;
+int rr_gather_rows(const rr_gather_item *host_items, int32_t count, const int64_t *idx, int32_t rows, void *stream);
+
 /* Parity-test hooks: per-environment dump of forward-pass intermediates (tests only). */
 int rr_debug_field(const rr_model *m, const char *name, int32_t *offset, int32_t *count);
 int rr_env_set_debug(rr_env *e, float *dbg /* DEVICE [B, debug_stride] or null */);

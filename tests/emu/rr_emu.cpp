@@ -218,6 +218,26 @@ static int rrb_launch_ppo_loss(const RRPpoLossArgs &a, void *) {
   return 0;
 }
 
+/* Adam and the minibatch gather: the same per-element arithmetic in plain loops */
+#define RR_MISC_HD static inline
+#include "../../brax_rodent_run_b200/csrc/rr_learner_misc.h"
+static int rrb_adam_step(float *p, const float *g, float *m, float *v, float *step, long long n, float lr, float b1, float b2,
+                         float eps, void *) {
+  const float t = step[0] + 1.f;
+  for (long long i = 0; i < n; i++) rr_adam_element(p[i], g[i], m[i], v[i], t, lr, b1, b2, eps);
+  step[0] = t;
+  return 0;
+}
+static int rrb_gather_rows(const RRGatherArgs &a, int, void *) {
+  for (int it = 0; it < a.count; it++) {
+    const rr_gather_item &g = a.item[it];
+    for (int t = 0; t < g.outer; t++)
+      for (int j = 0; j < a.rows; j++)
+        memcpy(g.dst + ((size_t)t * a.rows + j) * g.inner, g.src + ((size_t)t * g.src_rows + a.idx[j]) * g.inner, sizeof(float) * g.inner);
+  }
+  return 0;
+}
+
 /* the learner's grouped GEMM: plain loops with the contract of rr_tc_problem ("device" pointers are host pointers) */
 #define RR_TC_HD static inline
 #include "../../brax_rodent_run_b200/csrc/rr_tc_gemm.h"

@@ -179,10 +179,10 @@ def test_graphed_update_matches_eager_update():
     assert float((d_graph - d_eager).abs().max()) < 0.05 * cfg.learning_rate, float((d_graph - d_eager).abs().max())
 
 
-def _loss_case(emu_or_cuda_env, device, seed=0, T=5, B=37):
+def _loss_case(emu_or_cuda_env, device, seed=0, T=5, B=37, tc=False):
     """Random minibatch incl. terminations / truncations, a few saturated ratios and a large pre-softplus scale."""
     from brax_rodent_run_b200.ppo import PPO, PPOConfig
-    cfg = PPOConfig(**dict(TINY, num_envs=emu_or_cuda_env.num_envs, tf32=False, cuda_graph=False))
+    cfg = PPOConfig(**dict(TINY, num_envs=emu_or_cuda_env.num_envs, tf32=False, cuda_graph=False, tc_learner=tc))
     agent = PPO(emu_or_cuda_env, cfg)
     g = torch.Generator().manual_seed(seed)
     A, obs = emu_or_cuda_env.action_size, emu_or_cuda_env.observation_size
@@ -362,11 +362,11 @@ def dataclasses_asdict(cfg):
 def _compare_tc_with_autograd(agent, mb, tol):
     """loss_and_grads through the hand-written forward / backward (tc_learner.py on rr_tc_launch) against autograd."""
     outs = []
+    flat_views = [p.grad for p in agent.params]      # the agent was built with tc_learner=True: views of the flat gradient buffer
     for use_tc in (False, True):
         agent._use_tc = use_tc
-        if not use_tc:
-            for p in agent.params:
-                p.grad = None
+        for p, g in zip(agent.params, flat_views):
+            p.grad = g if use_tc else None
         metrics = agent.loss_and_grads(mb)
         outs.append(({k: float(v) for k, v in metrics.items()}, torch.cat([p.grad.reshape(-1) for p in agent.params]).cpu().clone(),
                      [p.grad.detach().cpu().clone() for p in agent.params]))
@@ -380,7 +380,7 @@ def _compare_tc_with_autograd(agent, mb, tol):
 
 
 def test_tc_learner_matches_autograd_on_emulator(emu_lib):
-    agent, mb = _loss_case(tiny_env(emu_lib), "cpu", seed=3, T=3, B=5)
+    agent, mb = _loss_case(tiny_env(emu_lib), "cpu", seed=3, T=3, B=5, tc=True)
     _compare_tc_with_autograd(agent, mb, 2e-4)
     assert agent._tc.launches_per_update == 3 + 2 + 1    # TINY: 3 forward layers, 2 dgrad steps, one wgrad launch
     assert agent._tc.splits == 1
@@ -388,7 +388,7 @@ def test_tc_learner_matches_autograd_on_emulator(emu_lib):
 
 def test_tc_learner_split_wgrad_on_emulator(emu_lib):
     """Enough rows for the weight gradients to be split four ways over the rows (partials + fixed-order sum)."""
-    agent, mb = _loss_case(tiny_env(emu_lib), "cpu", seed=4, T=4, B=256)
+    agent, mb = _loss_case(tiny_env(emu_lib), "cpu", seed=4, T=4, B=256, tc=True)
     _compare_tc_with_autograd(agent, mb, 5e-4)
     assert agent._tc.splits == 4
 
@@ -415,7 +415,7 @@ def test_tc_learner_matches_autograd_on_gpu():
     from brax_rodent_run_b200.env import Rodent
     from brax_rodent_run_b200.ppo import PPO, PPOConfig
     env = Rodent(synthetic_track(), num_envs=2, device="cuda:0", model=load_asset("rodent_0"), iterations=1, ls_iterations=1, n_frames=1)
-    cfg = PPOConfig(num_envs=2, batch_size=2, num_minibatches=2, unroll_length=2, cuda_graph=False, tf32=False)
+    cfg = PPOConfig(num_envs=2, batch_size=2, num_minibatches=2, unroll_length=2, cuda_graph=False, tf32=False, tc_learner=True)
     agent = PPO(env, cfg)
     _, mb = _loss_case(env, "cuda:0", seed=2, T=10, B=512)
     agent._batch_is_normalized = True
@@ -463,9 +463,10 @@ def test_graphed_tc_update_matches_eager_autograd_update():
         p.grad = None
     total, m = agent.loss(st)
     total.backward()
-    agent.opt.step()
-    for p, g in zip(agent.params, tc_grads):
+    for p, g in zip(agent.params, tc_grads):     # the optimizer steps over the flat gradient buffer
+        g.copy_(p.grad)
         p.grad = g
+    agent.opt.step()
     agent._use_tc = True
     d_eager = torch.cat([(p.detach() - v).reshape(-1) for p, v in zip(agent.params, saved)]).cpu()
     for k in m:

@@ -89,3 +89,53 @@ def test_strided_views_and_errors(backend, emu_lib):
         p = tc_gemm.problem(x, w, out[:, 52:100])
         p["epi"] = 2  # no aux_in
         tc_gemm.TcGroup(L, [p], dev)
+
+
+@pytest.mark.parametrize("backend", backend_params())
+def test_flat_adam_matches_torch_adam(backend, emu_lib):
+    """rr_adam_step: torch.optim.Adam's arithmetic (the reference's optax.adam) on a flat buffer, step counter on the device."""
+    from brax_rodent_run_b200.tc_learner import FlatAdam
+    L, dev, _ = _setup(backend, emu_lib)
+    g0 = torch.Generator().manual_seed(0)
+    p, g = torch.randn(70001, generator=g0).to(dev), torch.randn(70001, generator=g0).to(dev)
+    ref = torch.nn.Parameter(p.clone())
+    opt = torch.optim.Adam([ref], lr=3e-4, eps=1e-8)
+    fa = FlatAdam(L, p, g, 3e-4)
+    for _ in range(6):
+        ref.grad = g.clone()
+        opt.step()
+        fa.step()
+        g.mul_(0.7).add_(0.1)
+    assert float(fa.state[0]["step"]) == 6.0
+    assert float((p - ref.data).abs().max()) < 2e-6
+    sd = fa.state_dict()
+    fb = FlatAdam(L, p.clone(), g, 3e-4)
+    fb.load_state_dict(sd)
+    assert torch.equal(fb.state[0]["exp_avg"], fa.state[0]["exp_avg"]) and float(fb.state[0]["step"]) == 6.0
+
+
+@pytest.mark.parametrize("backend", backend_params())
+def test_gather_rows_matches_index_select(backend, emu_lib):
+    """rr_gather_rows: the learner's minibatch gather (seven tensors, one launch) against torch indexing."""
+    import ctypes
+    L, dev, _ = _setup(backend, emu_lib)
+    g0 = torch.Generator().manual_seed(1)
+    T, N, rows = 3, 50, 16
+    srcs = [torch.randn(T, N, 1264, generator=g0), torch.randn(T, N, 30, generator=g0), torch.randn(T, N, generator=g0),
+            torch.randn(N, 1264, generator=g0), torch.randn(T, N, 7, generator=g0)]
+    srcs = [s.to(dev) for s in srcs]
+    idx = torch.randperm(N, generator=g0)[:rows].to(dev)
+    dsts = [torch.zeros((s.shape[0], rows) + tuple(s.shape[2:]), device=dev) if i != 3 else torch.zeros(rows, 1264, device=dev)
+            for i, s in enumerate(srcs)]
+    items = (_lib.RRGatherItem * len(srcs))()
+    for i, (it, s, d) in enumerate(zip(items, srcs, dsts)):
+        lead = 1 if i == 3 else 2
+        it.src, it.dst = s.data_ptr(), d.data_ptr()
+        it.outer, it.src_rows = (1 if lead == 1 else s.shape[0]), s.shape[lead - 1]
+        it.inner = int(torch.tensor(s.shape[lead:]).prod()) if s.dim() > lead else 1
+    stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream) if dev.type == "cuda" else None
+    _lib.check(L, L.rr_gather_rows(items, len(srcs), ctypes.c_void_p(idx.data_ptr()), rows, stream))
+    for i, (s, d) in enumerate(zip(srcs, dsts)):
+        assert torch.equal(d, s[idx] if i == 3 else s[:, idx]), i
+    with pytest.raises(ValueError):
+        _lib.check(L, L.rr_gather_rows(items, 9, ctypes.c_void_p(idx.data_ptr()), rows, stream))
