@@ -62,7 +62,7 @@ class RRTcProblem(ctypes.Structure):
 
 class RRGatherItem(ctypes.Structure):
     """rr_gather_item (include/rr_b200.h)."""
-    _fields_ = [("src", vp), ("dst", vp)] + [(n, ctypes.c_int32) for n in ("outer", "src_rows", "inner", "reserved")]
+    _fields_ = [("src", vp), ("dst", vp)] + [(n, ctypes.c_int32) for n in ("outer", "src_rows", "inner", "dst_pitch")]
 
 
 _libs = {}

@@ -309,8 +309,8 @@ __global__ void rr_gather_kernel(const __grid_constant__ RRGatherArgs a) {
   const int r = blockIdx.x - a.block_start[it], t = r / a.rows, j = r % a.rows;
   const long long src_row = a.idx[j];
   const float *src = g.src + ((size_t)t * g.src_rows + src_row) * g.inner;
-  float *dst = g.dst + ((size_t)t * a.rows + j) * g.inner;
-  if ((g.inner & 3) == 0 && ((reinterpret_cast<uintptr_t>(g.src) | reinterpret_cast<uintptr_t>(g.dst)) & 15) == 0) {
+  float *dst = g.dst + ((size_t)t * a.rows + j) * g.dst_pitch;
+  if (((g.inner | g.dst_pitch) & 3) == 0 && ((reinterpret_cast<uintptr_t>(g.src) | reinterpret_cast<uintptr_t>(g.dst)) & 15) == 0) {
     const float4 *s4 = reinterpret_cast<const float4 *>(src);
     float4 *d4 = reinterpret_cast<float4 *>(dst);
     for (int i = threadIdx.x; i < g.inner / 4; i += blockDim.x) d4[i] = s4[i];

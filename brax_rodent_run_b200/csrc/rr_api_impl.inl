@@ -368,11 +368,13 @@ extern "C" int rr_tc_plan(rr_tc_problem *pr, int32_t count, int32_t *total_tiles
     rr_tc_problem &p = pr[i];
     if (p.m < 1 || p.n < 1 || p.k < 1 || !p.a || !p.b || !p.d) return rr_fail(RR_EINVAL, "rr_tc_plan: empty problem or null matrix");
     if (p.epi < 0 || p.epi > 2 || (p.epi == 2 && !p.aux_in)) return rr_fail(RR_EINVAL, "rr_tc_plan: bad epilogue");
-    if (p.b_ones && (!p.b_mn || !p.ones_out)) return rr_fail(RR_EINVAL, "rr_tc_plan: b_ones needs an MN-major B and ones_out");
-    if (p.lda < (p.a_mn ? p.m : p.k) || p.ldb < (p.b_mn ? p.n : p.k) || p.ldd < p.n ||
-        ((p.epi == 2 || (p.epi == 1 && p.aux_out)) && p.ldaux < p.n))
+    if (p.b_ones < 0 || p.b_ones > 2 || (p.b_ones && !p.ones_out) || (p.b_ones == 1 && !p.b_mn) || (p.b_ones == 2 && p.n < 2))
+      return rr_fail(RR_EINVAL, "rr_tc_plan: b_ones needs ones_out (and an MN-major B for the virtual row)");
+    const int n_d = p.n - (p.b_ones == 2 ? 1 : 0);
+    if (p.lda < (p.a_mn ? p.m : p.k) || p.ldb < (p.b_mn ? p.n : p.k) || p.ldd < n_d ||
+        ((p.epi == 2 || (p.epi == 1 && p.aux_out)) && p.ldaux < n_d))
       return rr_fail(RR_EINVAL, "rr_tc_plan: leading dimension smaller than the row length");
-    const int n_ext = p.n + (p.b_ones ? 1 : 0), tiles_m = (p.m + 127) / 128;
+    const int n_ext = n_d + (p.b_ones ? 1 : 0), tiles_m = (p.m + 127) / 128;
     /* 128-wide tiles halve the A traffic and the tensor core's shared-memory reads per flop; narrower only when n is */
     int bn = (n_ext + 15) / 16 * 16;
     if (bn > 128) bn = 128;
@@ -432,6 +434,8 @@ extern "C" int rr_gather_rows(const rr_gather_item *items, int32_t count, const 
     if (!items[i].src || !items[i].dst || items[i].outer < 1 || items[i].src_rows < 1 || items[i].inner < 1)
       return rr_fail(RR_EINVAL, "rr_gather_rows: bad item");
     a.item[i] = items[i];
+    if (a.item[i].dst_pitch == 0) a.item[i].dst_pitch = items[i].inner;
+    if (a.item[i].dst_pitch < items[i].inner) return rr_fail(RR_EINVAL, "rr_gather_rows: dst_pitch smaller than the row");
     a.block_start[i] = blocks;
     blocks += items[i].outer * rows;
   }

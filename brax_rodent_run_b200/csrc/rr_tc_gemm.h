@@ -55,14 +55,15 @@ RR_TC_HD float rr_tc_epilogue(const rr_tc_problem &p, int row, int col, float ac
 /* plain loops with the same semantics (fp32 products): emulator backend and documentation of the contract */
 static inline void rr_tc_reference(const rr_tc_problem &p) {
   for (int r = 0; r < p.m; r++) {
-    for (int c = 0; c < p.n + (p.b_ones ? 1 : 0); c++) {
+    const int n_d = p.n - (p.b_ones == 2 ? 1 : 0); /* columns of D; column n_d (virtual or B's real last row) -> ones_out */
+    for (int c = 0; c < n_d + (p.b_ones ? 1 : 0); c++) {
       float acc = 0.f;
       for (int kk = 0; kk < p.k; kk++) {
         const float av = p.a_mn ? p.a[(size_t)kk * p.lda + r] : p.a[(size_t)r * p.lda + kk];
-        const float bv = c == p.n ? 1.f : (p.b_mn ? p.b[(size_t)kk * p.ldb + c] : p.b[(size_t)c * p.ldb + kk]);
+        const float bv = (c == p.n && p.b_ones == 1) ? 1.f : (p.b_mn ? p.b[(size_t)kk * p.ldb + c] : p.b[(size_t)c * p.ldb + kk]);
         acc += av * bv;
       }
-      if (c == p.n) p.ones_out[r] = acc;
+      if (c == n_d && p.b_ones) p.ones_out[r] = acc;
       else p.d[(size_t)r * p.ldd + c] = rr_tc_epilogue(p, r, c, acc);
     }
   }
@@ -301,13 +302,14 @@ __global__ void __launch_bounds__(RR_TC_THREADS, 2) gemm_kernel(const RRTcRecord
   const int t = blockIdx.x - p.tile_start, tile_m = t / p.tiles_n, tile_n = t % p.tiles_n;
   const int BN = p.bn, K = p.k, nkb = (K + RR_TC_BK - 1) / RR_TC_BK;
   const int nst = p.reserved[3]; /* stages of this problem's ring (<= RR_TC_STAGES): what fits the launch's shared memory */
-  const int n_ext = p.n + (p.b_ones ? 1 : 0);
+  const int n_d = p.n - (p.b_ones == 2 ? 1 : 0); /* columns of D */
+  const int n_ext = n_d + (p.b_ones ? 1 : 0);   /* columns of the product: + the bias-gradient column */
 
   Operand oa, ob;
   oa.base = p.a; oa.rows = p.m; oa.ld = p.lda; oa.mn = p.a_mn; oa.row0 = tile_m * RR_TC_BM; oa.tile_rows = RR_TC_BM;
   oa.fast = (p.lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.a) & 15) == 0); oa.ones_row = -1;
   ob.base = p.b; ob.rows = p.n; ob.ld = p.ldb; ob.mn = p.b_mn; ob.row0 = tile_n * BN; ob.tile_rows = BN;
-  ob.fast = (p.ldb % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.b) & 15) == 0); ob.ones_row = p.b_ones ? p.n : -1;
+  ob.fast = (p.ldb % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.b) & 15) == 0); ob.ones_row = p.b_ones == 1 ? p.n : -1;
 
   const uint32_t smem0 = smem_u32(tc_smem);
   const uint32_t a_bytes = RR_TC_BM * RR_TC_BK * 4, b_bytes = p.b_mn ? (uint32_t)((BN + 31) >> 5) * 4096 : (uint32_t)BN * 128, stage_bytes = a_bytes + b_bytes;
@@ -316,7 +318,7 @@ __global__ void __launch_bounds__(RR_TC_THREADS, 2) gemm_kernel(const RRTcRecord
 
   if (tid < 128) {
     const int c = tile_n * BN + tid;
-    bias_s[tid] = (p.bias && tid < BN && c < p.n) ? p.bias[c] : 0.f;
+    bias_s[tid] = (p.bias && tid < BN && c < n_d) ? p.bias[c] : 0.f;
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(ncols) : "memory");
@@ -324,7 +326,7 @@ __global__ void __launch_bounds__(RR_TC_THREADS, 2) gemm_kernel(const RRTcRecord
   }
   /* TMA for an operand when the plan made a tensor map for it -- except for the B tile that carries the virtual row of ones */
   const bool tma_a = (p.reserved[2] & 1) != 0;
-  const bool tma_b = (p.reserved[2] & 2) != 0 && !(p.b_ones && ob.row0 + ((BN + 31) & ~31) > p.n);
+  const bool tma_b = (p.reserved[2] & 2) != 0 && !(p.b_ones == 1 && ob.row0 + ((BN + 31) & ~31) > p.n);
   const uint32_t tx_bytes = (tma_a ? a_bytes : 0u) + (tma_b ? b_bytes : 0u);
   const bool any_tma = tma_a || tma_b, any_cp = !tma_a || !tma_b;
   if (tid == 0) {
@@ -429,7 +431,7 @@ __global__ void __launch_bounds__(RR_TC_THREADS, 2) gemm_kernel(const RRTcRecord
   /* the SiLU-derivative epilogue reads the pre-activations: fetch them one 16-column group ahead of the accumulator */
   float4 aux_next[4] = {};
   const int jstep = RR_TC_THREADS / 128;
-  auto vec_group = [&](int j) { return row_ok && tile_n * BN + j * 16 + 16 <= p.n && vec_d && vec_aux; };
+  auto vec_group = [&](int j) { return row_ok && tile_n * BN + j * 16 + 16 <= n_d && vec_d && vec_aux; };
   auto fetch_aux = [&](int j) {
     const float4 *ap = reinterpret_cast<const float4 *>(p.aux_in + (size_t)row * p.ldaux + tile_n * BN + j * 16);
 #pragma unroll
@@ -484,8 +486,8 @@ __global__ void __launch_bounds__(RR_TC_THREADS, 2) gemm_kernel(const RRTcRecord
 #pragma unroll
       for (int i = 0; i < 16; i++) {
         const int c = c0 + i;
-        if (c < p.n) p.d[(size_t)row * p.ldd + c] = rr_tc_epilogue(p, row, c, __uint_as_float(v[i]));
-        else if (c == p.n && p.b_ones) p.ones_out[row] = __uint_as_float(v[i]);
+        if (c < n_d) p.d[(size_t)row * p.ldd + c] = rr_tc_epilogue(p, row, c, __uint_as_float(v[i]));
+        else if (c == n_d && p.b_ones) p.ones_out[row] = __uint_as_float(v[i]);
       }
     }
   }

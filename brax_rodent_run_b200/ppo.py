@@ -51,8 +51,9 @@ class PPOConfig:
     num_eval_envs: int = 128
     deterministic_eval: bool = False
     seed: int = 0
-    tc_learner: bool = False        # the two MLPs' forward / backward as 12 grouped tcgen05 GEMM launches (tc_learner.py) instead of
-                                    # autograd + cuBLAS (~95 launches); needs fused_loss
+    tc_learner: Optional[bool] = None  # the two MLPs' forward / backward as 12 grouped TMA + tcgen05 GEMM launches (tc_learner.py),
+                                    # Adam and the minibatch gather as own kernels, instead of autograd + cuBLAS (~95 launches);
+                                    # needs fused_loss.  None: on for CUDA devices, off on the CPU
     fused_loss: bool = True         # loss + gradient w.r.t. the network outputs in two hand-written kernels (rr_ppo_loss)
     cuda_graph: bool = True         # replay the minibatch update (loss, backward, Adam) as one CUDA graph on CUDA devices
     graph_allreduce: bool = False   # several ranks: capture the NCCL all-reduce + Adam in the update graph too.  OFF: with torch 2.11 /
@@ -247,8 +248,8 @@ class PPO:
         cuda = self.device.type == "cuda"
         # tensor-core learner (tc_learner.py): parameters, gradients and the Adam state live in flat buffers from the start (the
         # rollout graph captures the parameters' addresses); the GEMM launch lists are built at the first loss_and_grads() call
-        assert not cfg.tc_learner or cfg.fused_loss, "tc_learner needs fused_loss"
-        self._use_tc = bool(cfg.tc_learner)
+        self._use_tc = cuda if cfg.tc_learner is None else bool(cfg.tc_learner)
+        assert not self._use_tc or cfg.fused_loss, "tc_learner needs fused_loss"
         self._tc = None
         if self._use_tc:
             from .tc_learner import FlatAdam, flatten_parameters
@@ -410,7 +411,7 @@ class PPO:
             self._tc = TcLearner(self.env._L, self.policy, self.value, T * b, b, self.device, self._flat_g, self._flat_off)
         tc = self._tc
         if obs.data_ptr() != tc.x.data_ptr():
-            tc.x.copy_(obs.reshape(T * b, -1))
+            tc.x.copy_(obs.reshape(T * b, -1))      # tc.x is a pitched view (the buffer carries a column of ones)
         if nxt.data_ptr() != tc.xb.data_ptr():
             tc.xb.copy_(nxt.reshape(b, -1))
         tc.forward()
@@ -459,7 +460,7 @@ class PPO:
                 from .tc_learner import TcLearner
                 T, b = data["observation"].shape[0], cfg.batch_size
                 self._tc = TcLearner(self.env._L, self.policy, self.value, T * b, b, self.device, self._flat_g, self._flat_off)
-                self._static["observation"] = self._tc.x.view(T, b, -1)
+                self._static["observation"] = self._tc.x.unflatten(0, (T, b))   # pitched view: rows of k0 floats, pitch k0 + 4
                 self._static["next_observation_last"] = self._tc.xb
             # the batch the minibatches are gathered from and the minibatch's indices are static too, so that the gathers are
             # part of the graph (seven index_select launches per update were most of the host time of an update)
@@ -475,7 +476,7 @@ class PPO:
         def gather():
             if self._gather_items is None:  # one launch for all seven tensors (rr_gather_rows)
                 keys = list(batch)
-                assert all(batch[k].dtype == torch.float32 and batch[k].is_contiguous() and st[k].is_contiguous() for k in keys)
+                assert all(batch[k].dtype == torch.float32 and batch[k].is_contiguous() for k in keys)
                 items = (_lib.RRGatherItem * len(keys))()
                 for it, k in zip(items, keys):
                     v = batch[k]
@@ -484,6 +485,10 @@ class PPO:
                     it.outer = v.shape[0] if lead == 2 else 1
                     it.src_rows = v.shape[lead - 1]
                     it.inner = int(math.prod(v.shape[lead:]))
+                    d = st[k]                                                 # contiguous, or rows with a pitch (2-D inner only)
+                    it.dst_pitch = it.inner if d.is_contiguous() else d.stride(lead - 1)
+                    assert d.is_contiguous() or (d.dim() == lead + 1 and d.stride(-1) == 1 and
+                                                 (lead == 1 or d.stride(0) == d.shape[1] * d.stride(1)))
                 self._gather_items = items
             stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
             _lib.check(self.env._L, self.env._L.rr_gather_rows(self._gather_items, len(self._gather_items),

@@ -49,6 +49,8 @@ def main():
     ap.add_argument("--clip", default="clips/84.p")
     ap.add_argument("--out", default="./model_checkpoints")
     ap.add_argument("--eval-every", type=int, help="env steps between evaluations (config default: 5M)")
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--tc-learner", type=int, choices=(0, 1), help="tensor-core learner off / on (default: on)")
     a = ap.parse_args()
     config = dict(CONFIGS[a.config], env_name="rodent", algo_name="ppo", task_name="run")
     if a.num_timesteps:
@@ -73,7 +75,8 @@ def main():
     cfg = PPOConfig(num_timesteps=config["num_timesteps"], num_evals=max(1, int(config["num_timesteps"] / config["eval_every"])),
                     episode_length=config["episode_length"], num_envs=config["num_envs"], batch_size=config["batch_size"],
                     learning_rate=config["learning_rate"], unroll_length=10, num_minibatches=64, num_updates_per_batch=8,
-                    discounting=0.97, entropy_cost=1e-3, reward_scaling=1.0, normalize_observations=True, seed=0)
+                    discounting=0.97, entropy_cost=1e-3, reward_scaling=1.0, normalize_observations=True, seed=a.seed,
+                    tc_learner=None if a.tc_learner is None else bool(a.tc_learner))
     run_dir = os.path.join(a.out, str(uuid.uuid4()))
 
     def progress(num_steps, metrics):

@@ -17,26 +17,28 @@ EPI_LINEAR, EPI_SILU, EPI_DSILU = 0, 1, 2
 
 def problem(a: torch.Tensor, b: torch.Tensor, d: torch.Tensor, *, a_t: bool = False, b_t: bool = False,
             bias: Optional[torch.Tensor] = None, epi: int = EPI_LINEAR, aux_in: Optional[torch.Tensor] = None,
-            aux_out: Optional[torch.Tensor] = None, ones_out: Optional[torch.Tensor] = None) -> Dict:
+            aux_out: Optional[torch.Tensor] = None, ones_out: Optional[torch.Tensor] = None, ones_stored: bool = False) -> Dict:
     """D = epi(A B' + bias) with logical A [m, k], B [n, k].  `a` is A stored [m, k] (or A' stored [k, m] with a_t), `b` is B
     stored [n, k] (or B' stored [k, n] with b_t); all 2-D fp32 with unit stride along the last axis.  `ones_out` [m]: also
-    return the sum of A over k (needs b_t)."""
+    return the sum of A over k (needs b_t) -- or, with `ones_stored`, B's last row is a stored row of ones: D has n - 1 columns and
+    the product's last column goes to ones_out."""
     for t in (a, b, d, bias, aux_in, aux_out, ones_out):
         if t is not None:
             assert t.dtype == torch.float32 and (t.dim() == 1 or t.stride(-1) == 1), "fp32, unit stride along the last axis"
     m, k = (a.shape[1], a.shape[0]) if a_t else (a.shape[0], a.shape[1])
     n, kb = (b.shape[1], b.shape[0]) if b_t else (b.shape[0], b.shape[1])
-    assert k == kb and tuple(d.shape) == (m, n), (a.shape, b.shape, d.shape, a_t, b_t)
+    n_d = n - 1 if ones_stored else n
+    assert k == kb and tuple(d.shape) == (m, n_d), (a.shape, b.shape, d.shape, a_t, b_t)
     aux = aux_in if aux_in is not None else aux_out
     if aux is not None:
-        assert tuple(aux.shape) == (m, n)
+        assert tuple(aux.shape) == (m, n_d)
     if bias is not None:
-        assert bias.numel() == n
+        assert bias.numel() == n_d
     if ones_out is not None:
-        assert b_t and ones_out.numel() == m
+        assert (b_t or ones_stored) and ones_out.numel() == m
     return dict(a=a, b=b, d=d, bias=bias, aux_in=aux_in, aux_out=aux_out, ones_out=ones_out, m=m, n=n, k=k, lda=a.stride(0),
                 ldb=b.stride(0), ldd=d.stride(0), ldaux=aux.stride(0) if aux is not None else 0, a_mn=int(a_t), b_mn=int(b_t),
-                epi=epi, b_ones=int(ones_out is not None))
+                epi=epi, b_ones=(2 if ones_stored else 1) if ones_out is not None else 0)
 
 
 class TcGroup:

@@ -7,8 +7,8 @@ brax_rodent_run_ppo.py:97-114, 200) by 12 grouped launches:
   loss      2: rr_ppo_loss (d loss / d logits, d loss / d baseline)
   dgrad     5: dZ_{l-1} = (dZ_l W_l) * silu'(Z_{l-1}) for both nets per launch (W read MN-major: no transposed copy)
   wgrad     1: all eleven dW_l = dZ_l' X_l in one launch (each split four ways over the rows; the partial sums are added in a fixed
-               order by one torch.sum), db_l as the product's extra "ones" column; the parameters' .grad tensors are views of one
-               flat buffer, which is also the NCCL all-reduce bucket
+               order by one torch.sum); the activation buffers carry a column of ones, so [dW_l | db_l] = dZ_l' [X_l | 1] is one
+               product; the parameters' .grad tensors are views of one flat buffer, which is also the NCCL all-reduce bucket
 The parameters stay ordinary nn.Linear weights (acting, export and the optimizer are unchanged).
 """
 from __future__ import annotations
@@ -79,14 +79,25 @@ class TcLearner:
         k0 = self.lp[0].in_features
         assert self.lv[0].in_features == k0
         new = lambda r, c: torch.zeros(r, c, device=dev)
-        self.x, self.xb = new(M, k0), new(Mb, k0)
+
+        def with_ones(r, c):
+            """[r, c] activations stored with pitch c + 4 and a column of ones at index c: the weight-gradient launch reads
+            [activations | 1] as ONE operand (by TMA), which makes the bias gradient the product's last column."""
+            buf = new(r, c + 4)
+            buf[:, c] = 1.0
+            return buf[:, :c], buf[:, :c + 1]
+
+        self.x, self.x1 = with_ones(M, k0)      # x: [M, k0] view (what the forward reads / the gather fills), x1: [x | 1]
+        self.xb = new(Mb, k0)
         # activations (h), pre-activations (z) and their gradients (dz) of the hidden layers; the heads' outputs
-        self.hp = [new(M, l.out_features) for l in self.lp[:-1]]
-        self.zp = [torch.zeros_like(h) for h in self.hp]
-        self.dzp = [torch.zeros_like(h) for h in self.hp]
-        self.hv = [new(M, l.out_features) for l in self.lv[:-1]]
-        self.zv = [torch.zeros_like(h) for h in self.hv]
-        self.dzv = [torch.zeros_like(h) for h in self.hv]
+        hp = [with_ones(M, l.out_features) for l in self.lp[:-1]]
+        hv = [with_ones(M, l.out_features) for l in self.lv[:-1]]
+        self.hp, self.hp1 = [a for a, _ in hp], [b for _, b in hp]
+        self.hv, self.hv1 = [a for a, _ in hv], [b for _, b in hv]
+        self.zp = [new(M, l.out_features) for l in self.lp[:-1]]
+        self.dzp = [torch.zeros_like(z) for z in self.zp]
+        self.zv = [new(M, l.out_features) for l in self.lv[:-1]]
+        self.dzv = [torch.zeros_like(z) for z in self.zv]
         self.hb = [new(Mb, l.out_features) for l in self.lv[:-1]]
         self.logits, self.grad_logits = new(M, self.lp[-1].out_features), new(M, self.lp[-1].out_features)
         self.baseline, self.grad_baseline = new(M, 1), new(M, 1)
@@ -139,9 +150,9 @@ class TcLearner:
 
         self.ones_row = torch.ones(1, M, device=dev)
 
-        def wgrad(lins, dz, h, g_head, l, sp):
+        def wgrad(lins, dz, h, h1, g_head, l, sp):
             dz_l = g_head if l == len(lins) - 1 else dz[l]
-            inp = self.x if l == 0 else h[l - 1]
+            inp, inp1 = (self.x, self.x1) if l == 0 else (h[l - 1], h1[l - 1])
             w, b = lins[l].weight, lins[l].bias
             rows = slice(sp * (M // self.splits), (sp + 1) * (M // self.splits))
             ow, ob = self._grad_off[id(w)], self._grad_off[id(b)]
@@ -153,14 +164,14 @@ class TcLearner:
                 g_row = dz_l.view(1, M)
                 return [problem(inp[rows], g_row[:, rows], dw.view(-1, 1), a_t=True),
                         problem(g_row[:, rows], self.ones_row[:, rows], db.view(1, 1))]
-            return [problem(dz_l[rows], inp[rows], dw, a_t=True, b_t=True, ones_out=db)]
+            return [problem(dz_l[rows], inp1[rows], dw, a_t=True, b_t=True, ones_out=db, ones_stored=True)]
 
         probs = []
         for sp in range(self.splits):
             for l in range(len(self.lv)):
-                probs += wgrad(self.lv, self.dzv, self.hv, self.grad_baseline, l, sp)
+                probs += wgrad(self.lv, self.dzv, self.hv, self.hv1, self.grad_baseline, l, sp)
             for l in range(len(self.lp)):
-                probs += wgrad(self.lp, self.dzp, self.hp, self.grad_logits, l, sp)
+                probs += wgrad(self.lp, self.dzp, self.hp, self.hp1, self.grad_logits, l, sp)
         self.wgrad_group = TcGroup(L, probs, dev)
         self.launches_per_update = len(self.fwd_groups) + len(self.dgrad_groups) + 1
 

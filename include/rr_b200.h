@@ -152,8 +152,9 @@ int rr_ppo_loss(const rr_ppo_loss_args *args, void *stream);
  *   epi           0: D = acc + bias
  *                 1: z = acc + bias; aux_out (if given) = z; D = silu(z)
  *                 2: D = (acc + bias) * silu'(aux_in)         (dgrad through the previous layer's activation)
- *   b_ones        B gets a virtual extra row n of ones (MN-major B only): column n of the product, the sum of A over k --
- *                 the bias gradient when A = dY' -- goes to ones_out[m]
+ *   b_ones        1: B gets a virtual extra row n of ones (MN-major B only): column n of the product, the sum of A over k -- the
+ *                 bias gradient when A = dY' -- goes to ones_out[m].  2: B's LAST row (index n - 1) is that row of ones, stored in
+ *                 memory (the activation buffers carry a column of ones): D has n - 1 columns, column n - 1 goes to ones_out
  * rr_tc_plan validates a HOST array, fills bn / tile_start / tiles_n and writes one device record per problem (the planned problem
  * + TMA tensor maps of the operands whose base and pitch are 16-byte aligned; the others are fetched with cp.async);
  * rr_tc_launch takes a DEVICE copy of the records (so that the launch is capturable in a CUDA graph).  All matrices are DEVICE
@@ -179,12 +180,12 @@ int rr_tc_launch(const void *device_records, int32_t count, int32_t total_tiles,
 int rr_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, float *step, int64_t n, float lr, float beta1,
                  float beta2, float eps, void *stream);
 
-/* Minibatch gather of the learner: for every item, dst[t, j, :] = src[t, idx[j], :] (src [outer, src_rows, inner], dst
- * [outer, rows, inner], fp32, contiguous); one launch for all items (at most 8).  idx: DEVICE int64 [rows]. */
+/* Minibatch gather of the learner: for every item, dst[t, j, :] = src[t, idx[j], :] (src [outer, src_rows, inner] contiguous,
+ * dst [outer, rows, inner] with row pitch dst_pitch, fp32); one launch for all items (at most 8).  idx: DEVICE int64 [rows]. */
 typedef struct rr_gather_item {
   const float *src;
   float *dst;
-  int32_t outer, src_rows, inner, reserved;
+  int32_t outer, src_rows, inner, dst_pitch; /* dst_pitch: floats between dst rows (0 = inner) */
 } rr_gather_item;
 int rr_gather_rows(const rr_gather_item *host_items, int32_t count, const int64_t *idx, int32_t rows, void *stream);
 

@@ -233,7 +233,7 @@ static int rrb_gather_rows(const RRGatherArgs &a, int, void *) {
     const rr_gather_item &g = a.item[it];
     for (int t = 0; t < g.outer; t++)
       for (int j = 0; j < a.rows; j++)
-        memcpy(g.dst + ((size_t)t * a.rows + j) * g.inner, g.src + ((size_t)t * g.src_rows + a.idx[j]) * g.inner, sizeof(float) * g.inner);
+        memcpy(g.dst + ((size_t)t * a.rows + j) * g.dst_pitch, g.src + ((size_t)t * g.src_rows + a.idx[j]) * g.inner, sizeof(float) * g.inner);
   }
   return 0;
 }

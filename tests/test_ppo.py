@@ -124,7 +124,7 @@ def test_graphed_update_matches_eager_update():
     from brax_rodent_run_b200.env import Rodent
     from brax_rodent_run_b200.ppo import PPO, PPOConfig
     cfg = PPOConfig(num_envs=64, batch_size=16, num_minibatches=8, unroll_length=4, num_updates_per_batch=2, episode_length=50,
-                    num_timesteps=1, policy_hidden=(32, 32), value_hidden=(64, 64), tf32=False, cuda_graph=True)
+                    num_timesteps=1, policy_hidden=(32, 32), value_hidden=(64, 64), tf32=False, cuda_graph=True, tc_learner=False)
     env = Rodent(synthetic_track(), num_envs=64, device="cuda:0", model=load_asset("rodent_0"), iterations=4, ls_iterations=4,
                  terminate_when_unhealthy=False).wrap_for_training(cfg.episode_length)
     agent = PPO(env, cfg)

@@ -65,9 +65,17 @@ def test_dgrad_and_wgrad(backend, emu_lib, m, n, k):
     dx = torch.full((m, k), float("nan"), device=dev)
     dw = torch.full((n, k), float("nan"), device=dev)
     db = torch.full((n,), float("nan"), device=dev)
+    # the same weight gradient with the ones stored as a column of the activation buffer (pitch k + 4)
+    xbuf = torch.zeros(m, k + 4, device=dev)
+    xbuf[:, :k], xbuf[:, k] = x, 1.0
+    dw2 = torch.full((n, k), float("nan"), device=dev)
+    db2 = torch.full((n,), float("nan"), device=dev)
     grp = tc_gemm.TcGroup(L, [tc_gemm.problem(dy, w, dx, b_t=True, epi=tc_gemm.EPI_DSILU, aux_in=z),
-                              tc_gemm.problem(dy, x, dw, a_t=True, b_t=True, ones_out=db)], dev)
+                              tc_gemm.problem(dy, x, dw, a_t=True, b_t=True, ones_out=db),
+                              tc_gemm.problem(dy, xbuf[:, :k + 1], dw2, a_t=True, b_t=True, ones_out=db2, ones_stored=True)], dev)
     grp.launch()
+    _close(dw2.double(), dy.double().T @ x.double(), tol)
+    _close(db2.double(), dy.double().sum(0), tol, scale=float(dy.abs().sum(0).max()) / 10)
     _close(dx.double(), (dy.double() @ w.double()) * _silu_grad(z.double()), tol)
     _close(dw.double(), dy.double().T @ x.double(), tol)
     _close(db.double(), dy.double().sum(0), tol, scale=float(dy.abs().sum(0).max()) / 10)
