@@ -272,10 +272,75 @@ static int rrb_launch_gae(const float *rewards, const float *values, const float
   return rrb_check(cudaGetLastError(), "rr_gae_kernel launch");
 }
 
+/* Stage B with one WARP per (t, env) element and one lane per action (A <= 32): the thread-per-element kernel above walks the
+ * 30 actions twice with log / exp / tanh in every step on only 40 CTAs (33 us for the README minibatch); the same arithmetic
+ * spread over the lanes, the two sums over the actions by shuffles. */
+#define RR_PPO_WARPS 8
+__global__ void __launch_bounds__(32 * RR_PPO_WARPS) rr_ppo_loss_b_warp_kernel(const __grid_constant__ RRPpoLossArgs a) {
+  __shared__ float sh[3][RR_PPO_WARPS];
+  double s1 = 0.0, s2 = 0.0;
+  for (int k = 0; k < a.nblkA; k++) { s1 += a.adv_partial[2 * k]; s2 += a.adv_partial[2 * k + 1]; }
+  const double n = (double)a.T * (double)a.B, mean_d = s1 / n;
+  double var = s2 / n - mean_d * mean_d;
+  if (var < 0.0) var = 0.0;
+  const float mean = (float)mean_d, std_ = (float)sqrt(var);
+  const int warp = threadIdx.x >> 5, k = threadIdx.x & 31, A = a.A;
+  const size_t i = (size_t)blockIdx.x * RR_PPO_WARPS + warp;
+  float pol = 0.f, val = 0.f, ent = 0.f;
+  if (i < (size_t)a.T * a.B) {
+    const float invN = 1.f / ((float)a.T * (float)a.B);
+    const float adv = a.normalize_advantage ? (a.adv[i] - mean) / (std_ + 1e-8f) : a.adv[i];
+    const float *lg = a.logits + i * 2 * A, *raw = a.raw_action + i * A, *nz = a.noise + i * A;
+    const bool on = k < A;
+    const float loc = on ? lg[k] : 0.f, pre = on ? lg[A + k] : 0.f, rk = on ? raw[k] : 0.f, nk = on ? nz[k] : 0.f;
+    const float scale = rr_softplus(pre) + 1e-3f, is = 1.f / scale, z = (rk - loc) * is, lsc = logf(scale);
+    float lp = on ? -0.5f * z * z - lsc - RR_PPO_HALF_LOG_2PI - rr_log_det_tanh(rk) : 0.f;
+    const float raw_e = loc + scale * nk, th = tanhf(raw_e);
+    float e = on ? 0.5f + RR_PPO_HALF_LOG_2PI + lsc + rr_log_det_tanh(raw_e) : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lp += __shfl_xor_sync(0xffffffffu, lp, o);
+      e += __shfl_xor_sync(0xffffffffu, e, o);
+    }
+    const float rho = expf(lp - a.old_log_prob[i]);
+    const float lo = 1.f - a.clip_eps, hi = 1.f + a.clip_eps;
+    const float t1 = rho * adv, t2 = fminf(fmaxf(rho, lo), hi) * adv;
+    const float g = (t1 <= t2) ? -adv * rho * invN : 0.f;
+    const float d = a.vs[i] - a.baseline[i];
+    const float ce = -a.entropy_cost * invN;
+    if (on) {
+      const float sig = pre > 20.f ? 1.f : 1.f / (1.f + expf(-pre));
+      float *gl = a.grad_logits + i * 2 * A;
+      gl[k] = g * z * is + ce * (-2.f * th);
+      gl[A + k] = (g * (z * z - 1.f) * is + ce * (is - 2.f * th * nk)) * sig;
+    }
+    if (k == 0) {
+      a.lp[i] = lp;
+      a.grad_baseline[i] = -0.5f * d * invN;
+    }
+    pol = -fminf(t1, t2); val = 0.25f * d * d; ent = e;
+  }
+  if (k == 0) { sh[0][warp] = pol; sh[1][warp] = val; sh[2][warp] = ent; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    float acc = 0.f;
+    for (int w = 0; w < RR_PPO_WARPS; w++) acc += sh[threadIdx.x][w];
+    a.loss_partial[3 * blockIdx.x + threadIdx.x] = acc;
+  }
+}
+
 static int rrb_ppo_blocks(int n) { return (n + RR_PPO_THREADS - 1) / RR_PPO_THREADS; }
+/* stage-B partial-sum rows the caller provides: the warp-per-element kernel's block count (>= the thread-per-element one's) */
+static int rrb_ppo_blocks_b(int n) { return (n + RR_PPO_WARPS - 1) / RR_PPO_WARPS; }
 static int rrb_launch_ppo_loss(const RRPpoLossArgs &a, void *stream) {
   rr_ppo_loss_a_kernel<<<rrb_ppo_blocks(a.B), RR_PPO_THREADS, 0, (cudaStream_t)stream>>>(a);
-  rr_ppo_loss_b_kernel<<<rrb_ppo_blocks(a.T * a.B), RR_PPO_THREADS, 0, (cudaStream_t)stream>>>(a);
+  if (a.A <= 32) {
+    rr_ppo_loss_b_warp_kernel<<<rrb_ppo_blocks_b(a.T * a.B), 32 * RR_PPO_WARPS, 0, (cudaStream_t)stream>>>(a);
+  } else { /* wide action spaces: thread per element; the partial-sum rows it does not write are zeroed */
+    const int used = rrb_ppo_blocks(a.T * a.B), rows = rrb_ppo_blocks_b(a.T * a.B);
+    if (rows > used) cudaMemsetAsync(a.loss_partial + 3 * (size_t)used, 0, sizeof(float) * 3 * (size_t)(rows - used), (cudaStream_t)stream);
+    rr_ppo_loss_b_kernel<<<used, RR_PPO_THREADS, 0, (cudaStream_t)stream>>>(a);
+  }
   return rrb_check(cudaGetLastError(), "rr_ppo_loss launch");
 }
 

@@ -332,7 +332,7 @@ extern "C" int rr_gae(const float *rewards, const float *values, const float *bo
 extern "C" int rr_ppo_loss_blocks(int32_t T, int32_t B, int32_t *blocks_a, int32_t *blocks_b) {
   if (T < 1 || B < 1 || !blocks_a || !blocks_b) return rr_fail(RR_EINVAL, "rr_ppo_loss_blocks: bad argument");
   *blocks_a = rrb_ppo_blocks(B);
-  *blocks_b = rrb_ppo_blocks(T * B);
+  *blocks_b = rrb_ppo_blocks_b(T * B);
   return RR_OK;
 }
 

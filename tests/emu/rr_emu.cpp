@@ -189,6 +189,7 @@ static int rrb_launch_gae(const float *rewards, const float *values, const float
 #define RR_PPO_HD static inline
 #include "../../brax_rodent_run_b200/csrc/rr_ppo_loss.h"
 static int rrb_ppo_blocks(int n) { return (n + 127) / 128; }
+static int rrb_ppo_blocks_b(int n) { return rrb_ppo_blocks(n); }
 static int rrb_launch_ppo_loss(const RRPpoLossArgs &a, void *) {
   /* same block decomposition and per-block sums as the CUDA kernels (sequential inside a block) */
   for (int blk = 0; blk < rrb_ppo_blocks(a.B); blk++) {
