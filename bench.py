@@ -403,6 +403,9 @@ def measure_extra(args, dev, world, rank):
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         out["ppo_train_sps"] = {"value": (agent.env_steps - e0) / float(dt.item()), "unit": "env-steps/s", "envs_per_gpu": 2048,
                                 "n_gpus": world, "training_steps": 3,
+                                "learner": ("tcgen05: %d grouped TMA + tcgen05.mma TF32 GEMM launches per minibatch update, own Adam / gather / loss "
+                                            "kernels (DESIGN.md section 11)" % agent._tc.launches_per_update) if agent._tc is not None
+                                else "autograd + cuBLAS TF32",
                                 "config": "readme.md:17-31: unroll 10, batch 512 x 64 minibatches, 8 epochs, CG 8/8, normalised obs"}
         del agent, env, state
     except Exception as ex:  # the contract line must survive a failure of an extra

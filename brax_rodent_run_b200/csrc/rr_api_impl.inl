@@ -362,7 +362,7 @@ extern "C" int rr_ppo_loss(const rr_ppo_loss_args *u, void *stream) {
 extern "C" int32_t rr_tc_record_bytes(void) { return (int32_t)sizeof(RRTcRecord); }
 
 extern "C" int rr_tc_plan(rr_tc_problem *pr, int32_t count, int32_t *total_tiles, int32_t *smem_bytes, void *records) {
-  if (!pr || count < 1 || count > 64 || !total_tiles || !smem_bytes || !records) return rr_fail(RR_EINVAL, "rr_tc_plan: bad argument");
+  if (!pr || count < 1 || count > 256 || !total_tiles || !smem_bytes || !records) return rr_fail(RR_EINVAL, "rr_tc_plan: bad argument");
   int tiles = 0;
   for (int i = 0; i < count; i++) {
     rr_tc_problem &p = pr[i];

@@ -13,6 +13,7 @@ and the metrics -- the `lax.pmean / psum` calls of brax's pmap'd train step.
 """
 from __future__ import annotations
 
+import collections.abc
 import ctypes
 import dataclasses
 import math
@@ -224,6 +225,33 @@ class _FusedPPOLoss(torch.autograd.Function):
         return g_total * grad_logits, g_total * grad_baseline, None, None, None, None, None
 
 
+class _LazyLossMetrics(collections.abc.Mapping):
+    """The loss terms of an update, formed from the loss kernel's per-block sums only when somebody reads them: inside the
+    captured update they would be five more launches per minibatch for numbers that are read once per training step."""
+
+    _KEYS = ("total_loss", "policy_loss", "v_loss", "entropy_loss")
+
+    def __init__(self, loss_partial, n, entropy_cost):
+        self._partial, self._n, self._ec = loss_partial, float(n), entropy_cost
+
+    def _terms(self):
+        t = self._partial.sum(0) / self._n
+        policy_loss, v_loss, entropy_loss = t[0], t[1], -self._ec * t[2]
+        return dict(total_loss=policy_loss + v_loss + entropy_loss, policy_loss=policy_loss, v_loss=v_loss, entropy_loss=entropy_loss)
+
+    def __getitem__(self, k):
+        return self._terms()[k]
+
+    def __iter__(self):
+        return iter(self._KEYS)
+
+    def __len__(self):
+        return len(self._KEYS)
+
+    def items(self):
+        return self._terms().items()
+
+
 class PPO:
     def __init__(self, env: Rodent, cfg: PPOConfig):
         self.env, self.cfg = env, cfg
@@ -421,9 +449,7 @@ class PPO:
         loss_partial, _, _ = launch_ppo_loss(self.env._L, cfg, tc.logits.view(T, b, -1), tc.baseline.view(T, b), tc.bootstrap.view(b),
                                              mb, noise, tc.grad_logits, tc.grad_baseline)
         tc.backward()
-        terms = loss_partial.sum(0) / float(T * b)
-        policy_loss, v_loss, entropy_loss = terms[0], terms[1], -cfg.entropy_cost * terms[2]
-        return dict(total_loss=policy_loss + v_loss + entropy_loss, policy_loss=policy_loss, v_loss=v_loss, entropy_loss=entropy_loss)
+        return _LazyLossMetrics(loss_partial, T * b, cfg.entropy_cost)
 
     def _allreduce_grads(self):
         """lax.pmean(grads): one flat fp32 bucket (2.53 MB for the rodent networks) per minibatch over NCCL."""
