@@ -75,16 +75,16 @@ def test_training_step_runs_and_learns_shapes(emu_lib):
     assert all(math.isfinite(float(v)) for v in metrics.values()), metrics
 
 
-def _rank_main(rank, world, port, emu_lib, out):
+def _rank_main(rank, world, port, emu_lib, out, tc=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from brax_rodent_run_b200.ppo import PPO, PPOConfig
-    cfg = PPOConfig(**TINY)
+    cfg = PPOConfig(**dict(TINY, tc_learner=tc))
     env = tiny_env(emu_lib).wrap_for_training(cfg.episode_length)
     agent = PPO(env, cfg)
     state = env.reset(100 + rank)  # per-rank env shard: different seeds
     # the normaliser is exercised (and all-reduced) but not applied: 16 samples give a degenerate std (see above)
-    agent.cfg = PPOConfig(**dict(TINY, normalize_observations=False))
+    agent.cfg = PPOConfig(**dict(TINY, normalize_observations=False, tc_learner=tc))
     agent.normalizer.update(state.obs, distributed=True)
     state, _ = agent.training_step(state)
     flat = torch.cat([p.detach().reshape(-1) for p in agent.params])
@@ -99,13 +99,15 @@ def _rank_main(rank, world, port, emu_lib, out):
     dist.destroy_process_group()
 
 
-def test_two_rank_gloo_training_step(emu_lib):
+@pytest.mark.parametrize("tc", [False, True], ids=["autograd", "tc_learner"])
+def test_two_rank_gloo_training_step(emu_lib, tc):
     """Ranks hold different env shards; after a training step the parameters and the normaliser must be identical on both
-    ranks (gradient all-reduce mean, normaliser moment all-reduce), and the counters are global."""
+    ranks (gradient all-reduce mean, normaliser moment all-reduce), and the counters are global.  With the tensor-core learner's
+    launch lists (emulator backend) the all-reduce runs on the flat gradient buffer itself."""
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + os.getpid() % 500
-    procs = [ctx.Process(target=_rank_main, args=(r, 2, port, emu_lib, q)) for r in range(2)]
+    port = 29500 + (os.getpid() + (250 if tc else 0)) % 500
+    procs = [ctx.Process(target=_rank_main, args=(r, 2, port, emu_lib, q, tc)) for r in range(2)]
     for p in procs:
         p.start()
     same_params, same_norm, count, env_steps = q.get(timeout=600)
