@@ -147,3 +147,30 @@ def test_gather_rows_matches_index_select(backend, emu_lib):
         assert torch.equal(d, s[idx] if i == 3 else s[:, idx]), i
     with pytest.raises(ValueError):
         _lib.check(L, L.rr_gather_rows(items, 9, ctypes.c_void_p(idx.data_ptr()), rows, stream))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("m,n,k", [(256, 256, 1264), (200, 60, 96), (130, 1, 256)])
+def test_cp_async_fallback_path(emu_lib, monkeypatch, m, n, k):
+    """Without tensor maps (RR_TC_NO_TMA: what happens when the driver entry point is unavailable, and what unaligned operands
+    always take) every operand is staged by cp.async into the same swizzled layouts: interior, ragged-row and generic loaders."""
+    L, dev, tol = _setup("cuda", emu_lib)
+    g = torch.Generator().manual_seed(m + n + k)
+    x = torch.randn(m, k, generator=g).to(dev)
+    w = (torch.randn(n, k, generator=g) / k ** 0.5).to(dev)
+    dy = torch.randn(m, n, generator=g).to(dev)
+    b = torch.randn(n, generator=g).to(dev)
+    y, dx = torch.empty(m, n, device=dev), torch.empty(m, k, device=dev)
+    dw, db = torch.empty(n, k, device=dev), torch.empty(n, device=dev)
+    probs = lambda: [tc_gemm.problem(x, w, y, bias=b), tc_gemm.problem(dy, w, dx, b_t=True),
+                     tc_gemm.problem(dy, x, dw, a_t=True, b_t=True, ones_out=db)]
+    with_tma = tc_gemm.TcGroup(L, probs(), dev)
+    monkeypatch.setenv("RR_TC_NO_TMA", "1")
+    grp = tc_gemm.TcGroup(L, probs(), dev)
+    assert all(a == 0 and bb == 0 for a, bb in grp.tma)
+    assert any(a or bb for a, bb in with_tma.tma) or k % 4 != 0
+    grp.launch()
+    _close(y.double(), x.double() @ w.double().T + b.double(), tol)
+    _close(dx.double(), dy.double() @ w.double(), tol)
+    _close(dw.double(), dy.double().T @ x.double(), tol)
+    _close(db.double(), dy.double().sum(0), tol, scale=float(dy.abs().sum(0).max()) / 10)
