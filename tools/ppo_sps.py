@@ -36,5 +36,5 @@ dt = time.perf_counter() - t0
 steps = agent.env_steps - e0
 print(json.dumps({"metric": "PPO train SPS", "value": steps / dt, "unit": "env-steps/s", "envs": a.envs, "train_steps": a.train_steps,
                   "env_steps_per_train_step": steps // a.train_steps, "s_per_train_step": dt / a.train_steps,
-                  "tc_learner": cfg.tc_learner, "rollout_s": t_roll, "learner_s": dt / a.train_steps - t_roll,
+                  "tc_learner": agent._use_tc, "rollout_s": t_roll, "learner_s": dt / a.train_steps - t_roll,
                   "config": "README: batch 512, 64 minibatches, unroll 10, 8 epochs, CG 8/8, normalize obs"}))

@@ -24,7 +24,7 @@ if a.replay_only:
         agent._graph.replay()
     torch.cuda.synchronize()
     sys.exit(0)
-out = {"tc_learner": cfg.tc_learner}
+out = {"tc_learner": agent._use_tc}
 # (a) device time of the update graph
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 n = 200
