@@ -310,12 +310,14 @@ def test_train_callback_gets_make_policy_like_brax(emu_lib):
     assert a.shape == (2, env.action_size)
 
 
-def test_resume_is_bitwise(emu_lib):
+@pytest.mark.parametrize("tc", [False, True], ids=["autograd", "tc_learner"])
+def test_resume_is_bitwise(emu_lib, tc):
     """Checkpoint / resume: state_dict -> load_state_dict into a fresh agent (same generator state, same env state) continues
-    bit-for-bit: the next training step gives identical parameters and losses."""
+    bit-for-bit: the next training step gives identical parameters and losses.  With the tensor-core learner the parameters are
+    views of a flat buffer and the optimizer state is FlatAdam's."""
     import copy
     from brax_rodent_run_b200.ppo import PPO, PPOConfig
-    cfg = PPOConfig(**dict(TINY, normalize_observations=False))
+    cfg = PPOConfig(**dict(TINY, normalize_observations=False, tc_learner=tc))
     env = tiny_env(emu_lib).wrap_for_training(cfg.episode_length)
     a = PPO(env, cfg)
     state = env.reset(0)
