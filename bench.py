@@ -401,7 +401,17 @@ def measure_extra(args, dev, world, rank):
         dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        update_us = None
+        if getattr(agent, "_graph", None) is not None:   # device time of one captured minibatch update (replays of the graph)
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            for _ in range(50):
+                agent._graph.replay()
+            ev1.record()
+            torch.cuda.synchronize(dev)
+            update_us = ev0.elapsed_time(ev1) / 50 * 1e3
         out["ppo_train_sps"] = {"value": (agent.env_steps - e0) / float(dt.item()), "unit": "env-steps/s", "envs_per_gpu": 2048,
+                                "update_graph_us": update_us,
                                 "n_gpus": world, "training_steps": 3,
                                 "learner": ("tcgen05: %d grouped TMA + tcgen05.mma TF32 GEMM launches per minibatch update, own Adam / gather / loss "
                                             "kernels (DESIGN.md section 11)" % agent._tc.launches_per_update) if agent._tc is not None
