@@ -83,6 +83,30 @@ __global__ void __launch_bounds__(32 * RRMaxWpb<NS>::value, 1) rr_step_kernel(co
   }
 }
 
+/* Programmatic dependent launch for the learner's small kernels: each starts with RR_PDL_PROLOGUE (wait for everything the stream
+ * produced, then let the next kernel of the stream begin its own launch / prologue), and is launched with the stream-serialisation
+ * attribute, which hides the launch latency between the ~18 dependent launches of a minibatch update.  RR_TC_NO_PDL=1: plain launches. */
+#define RR_PDL_PROLOGUE()                                      \
+  do {                                                         \
+    asm volatile("griddepcontrol.wait;" ::: "memory");         \
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); \
+  } while (0)
+template <typename... KArgs, typename... Args>
+static cudaError_t rr_launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, void *stream, Args... args) {
+  static const bool pdl = getenv("RR_TC_NO_PDL") == nullptr && getenv("RR_TC_NO_PDL_SMALL") == nullptr;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 /* ppo.losses.compute_gae: one thread per environment, reverse scan over the unroll (T = 10 in the reference). */
 __global__ void rr_gae_kernel(const float *__restrict__ rewards, const float *__restrict__ values,
                               const float *__restrict__ bootstrap, const float *__restrict__ termination,
@@ -109,6 +133,7 @@ __global__ void rr_gae_kernel(const float *__restrict__ rewards, const float *__
 #define RR_PPO_THREADS 128
 __global__ void __launch_bounds__(RR_PPO_THREADS) rr_ppo_loss_a_kernel(const __grid_constant__ RRPpoLossArgs a) {
   __shared__ double sh1[RR_PPO_THREADS], sh2[RR_PPO_THREADS];
+  RR_PDL_PROLOGUE();
   const int b = blockIdx.x * RR_PPO_THREADS + threadIdx.x;
   double s1 = 0.0, s2 = 0.0;
   if (b < a.B) rr_ppo_stage_a(a, b, s1, s2);
@@ -122,6 +147,7 @@ __global__ void __launch_bounds__(RR_PPO_THREADS) rr_ppo_loss_a_kernel(const __g
 }
 __global__ void __launch_bounds__(RR_PPO_THREADS) rr_ppo_loss_b_kernel(const __grid_constant__ RRPpoLossArgs a) {
   __shared__ float sh[3][RR_PPO_THREADS];
+  RR_PDL_PROLOGUE();
   double s1 = 0.0, s2 = 0.0;
   for (int k = 0; k < a.nblkA; k++) { s1 += a.adv_partial[2 * k]; s2 += a.adv_partial[2 * k + 1]; }
   const double n = (double)a.T * (double)a.B, mean = s1 / n;
@@ -278,6 +304,7 @@ static int rrb_launch_gae(const float *rewards, const float *values, const float
 #define RR_PPO_WARPS 8
 __global__ void __launch_bounds__(32 * RR_PPO_WARPS) rr_ppo_loss_b_warp_kernel(const __grid_constant__ RRPpoLossArgs a) {
   __shared__ float sh[3][RR_PPO_WARPS];
+  RR_PDL_PROLOGUE();
   double s1 = 0.0, s2 = 0.0;
   for (int k = 0; k < a.nblkA; k++) { s1 += a.adv_partial[2 * k]; s2 += a.adv_partial[2 * k + 1]; }
   const double n = (double)a.T * (double)a.B, mean_d = s1 / n;
@@ -333,9 +360,10 @@ static int rrb_ppo_blocks(int n) { return (n + RR_PPO_THREADS - 1) / RR_PPO_THRE
 /* stage-B partial-sum rows the caller provides: the warp-per-element kernel's block count (>= the thread-per-element one's) */
 static int rrb_ppo_blocks_b(int n) { return (n + RR_PPO_WARPS - 1) / RR_PPO_WARPS; }
 static int rrb_launch_ppo_loss(const RRPpoLossArgs &a, void *stream) {
-  rr_ppo_loss_a_kernel<<<rrb_ppo_blocks(a.B), RR_PPO_THREADS, 0, (cudaStream_t)stream>>>(a);
+  if (rrb_check(rr_launch_pdl(rr_ppo_loss_a_kernel, rrb_ppo_blocks(a.B), RR_PPO_THREADS, 0, stream, a), "rr_ppo_loss_a launch")) return 1;
   if (a.A <= 32) {
-    rr_ppo_loss_b_warp_kernel<<<rrb_ppo_blocks_b(a.T * a.B), 32 * RR_PPO_WARPS, 0, (cudaStream_t)stream>>>(a);
+    if (rrb_check(rr_launch_pdl(rr_ppo_loss_b_warp_kernel, rrb_ppo_blocks_b(a.T * a.B), 32 * RR_PPO_WARPS, 0, stream, a), "rr_ppo_loss_b launch"))
+      return 1;
   } else { /* wide action spaces: thread per element; the partial-sum rows it does not write are zeroed */
     const int used = rrb_ppo_blocks(a.T * a.B), rows = rrb_ppo_blocks_b(a.T * a.B);
     if (rows > used) cudaMemsetAsync(a.loss_partial + 3 * (size_t)used, 0, sizeof(float) * 3 * (size_t)(rows - used), (cudaStream_t)stream);
@@ -349,6 +377,7 @@ static int rrb_launch_ppo_loss(const RRPpoLossArgs &a, void *stream) {
 #include "rr_learner_misc.h"
 __global__ void rr_adam_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v,
                                const float *__restrict__ step, long long n, float lr, float b1, float b2, float eps) {
+  RR_PDL_PROLOGUE();
   const float t = step[0] + 1.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float pi = p[i], mi = m[i], vi = v[i];
@@ -356,17 +385,21 @@ __global__ void rr_adam_kernel(float *__restrict__ p, const float *__restrict__ 
     p[i] = pi; m[i] = mi; v[i] = vi;
   }
 }
-__global__ void rr_adam_step_inc_kernel(float *step) { step[0] += 1.f; }
+__global__ void rr_adam_step_inc_kernel(float *step) {
+  RR_PDL_PROLOGUE();
+  step[0] += 1.f;
+}
 static int rrb_adam_step(float *p, const float *g, float *m, float *v, float *step, long long n, float lr, float b1, float b2,
                          float eps, void *stream) {
   long long blocks = (n + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  rr_adam_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, step, n, lr, b1, b2, eps);
-  rr_adam_step_inc_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step);
-  return rrb_check(cudaGetLastError(), "rr_adam_kernel launch");
+  if (rrb_check(rr_launch_pdl(rr_adam_kernel, (int)blocks, 256, 0, stream, p, g, m, v, (const float *)step, n, lr, b1, b2, eps), "rr_adam_kernel launch"))
+    return 1;
+  return rrb_check(rr_launch_pdl(rr_adam_step_inc_kernel, 1, 1, 0, stream, step), "rr_adam_step_inc_kernel launch");
 }
 /* one block per gathered row: dst[t, j, :] = src[t, idx[j], :] */
 __global__ void rr_gather_kernel(const __grid_constant__ RRGatherArgs a) {
+  RR_PDL_PROLOGUE();
   int it = 0;
   for (int i = 1; i < a.count; i++)
     if ((int)blockIdx.x >= a.block_start[i]) it = i;
@@ -384,8 +417,7 @@ __global__ void rr_gather_kernel(const __grid_constant__ RRGatherArgs a) {
   }
 }
 static int rrb_gather_rows(const RRGatherArgs &a, int blocks, void *stream) {
-  rr_gather_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(a);
-  return rrb_check(cudaGetLastError(), "rr_gather_kernel launch");
+  return rrb_check(rr_launch_pdl(rr_gather_kernel, blocks, 128, 0, stream, a), "rr_gather_kernel launch");
 }
 
 /* grouped TF32 GEMM of the learner on the tensor cores (tcgen05) */
@@ -450,8 +482,21 @@ static int rrb_tc_launch(const RRTcRecord *dev_recs, int count, int total_tiles,
       return 1;
     configured[dev].store(true, std::memory_order_release);
   }
-  rr_tc::gemm_kernel<<<total_tiles, RR_TC_THREADS, smem_bytes, (cudaStream_t)stream>>>(dev_recs, count);
-  return rrb_check(cudaGetLastError(), "rr_tc gemm_kernel launch");
+  /* Programmatic dependent launch: the kernel's prologue (problem lookup, TMEM allocation, mbarrier initialisation) may start
+   * while the previous kernel of the stream drains; it executes griddepcontrol.wait before it touches anything the stream
+   * produced.  RR_TC_NO_PDL=1 launches plainly. */
+  static const bool pdl = getenv("RR_TC_NO_PDL") == nullptr;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)total_tiles);
+  cfg.blockDim = dim3(RR_TC_THREADS);
+  cfg.dynamicSmemBytes = (size_t)smem_bytes;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return rrb_check(cudaLaunchKernelEx(&cfg, rr_tc::gemm_kernel, dev_recs, count), "rr_tc gemm_kernel launch");
 }
 
 #include "rr_api_impl.inl"

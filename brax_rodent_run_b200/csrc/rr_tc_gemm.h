@@ -316,10 +316,6 @@ __global__ void __launch_bounds__(RR_TC_THREADS, 2) gemm_kernel(const RRTcRecord
   uint32_t ncols = 32;
   while ((int)ncols < BN) ncols <<= 1;
 
-  if (tid < 128) {
-    const int c = tile_n * BN + tid;
-    bias_s[tid] = (p.bias && tid < BN && c < n_d) ? p.bias[c] : 0.f;
-  }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(ncols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -336,6 +332,14 @@ __global__ void __launch_bounds__(RR_TC_THREADS, 2) gemm_kernel(const RRTcRecord
     }
     mbar_init(smem_u32(&done_bar), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  /* everything above touched only the launch's own records: under programmatic dependent launch it overlaps the tail of the
+   * previous kernel of the stream.  From here on the kernel reads what the stream produced. */
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (tid < 128) {
+    const int c = tile_n * BN + tid;
+    bias_s[tid] = (p.bias && tid < BN && c < n_d) ? p.bias[c] : 0.f;
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
