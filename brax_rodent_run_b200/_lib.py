@@ -108,6 +108,8 @@ def load(path: Optional[str] = None):
     L.rr_launch_count.restype = ctypes.c_longlong
     L.rr_adam_step.argtypes = [vp, vp, vp, vp, vp, ctypes.c_int64] + [ctypes.c_float] * 4 + [vp]
     L.rr_adam_step.restype = ctypes.c_int
+    L.rr_adam_step_sum.argtypes = [vp, vp, vp, ctypes.c_int32, vp, vp, vp, ctypes.c_int64] + [ctypes.c_float] * 4 + [vp]
+    L.rr_adam_step_sum.restype = ctypes.c_int
     L.rr_gather_rows.argtypes = [ctypes.POINTER(RRGatherItem), ctypes.c_int32, vp, ctypes.c_int32, vp]
     L.rr_gather_rows.restype = ctypes.c_int
     L.rr_tc_record_bytes.restype = ctypes.c_int32

@@ -375,13 +375,20 @@ static int rrb_launch_ppo_loss(const RRPpoLossArgs &a, void *stream) {
 /* ---- Adam on the flat parameter buffer, minibatch gather (rr_learner_misc.h) ---- */
 #define RR_MISC_HD __host__ __device__ static inline
 #include "rr_learner_misc.h"
-__global__ void rr_adam_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v,
-                               const float *__restrict__ step, long long n, float lr, float b1, float b2, float eps) {
+__global__ void rr_adam_kernel(float *__restrict__ p, float *__restrict__ g, const float *__restrict__ partials, int nsplit,
+                               float *__restrict__ m, float *__restrict__ v, const float *__restrict__ step, long long n, float lr,
+                               float b1, float b2, float eps) {
   RR_PDL_PROLOGUE();
   const float t = step[0] + 1.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float gi;
+    if (partials) { /* the split weight-gradient launch's partial sums, added in a fixed order */
+      gi = partials[i];
+      for (int s = 1; s < nsplit; s++) gi += partials[(size_t)s * n + i];
+      g[i] = gi;
+    } else gi = g[i];
     float pi = p[i], mi = m[i], vi = v[i];
-    rr_adam_element(pi, g[i], mi, vi, t, lr, b1, b2, eps);
+    rr_adam_element(pi, gi, mi, vi, t, lr, b1, b2, eps);
     p[i] = pi; m[i] = mi; v[i] = vi;
   }
 }
@@ -389,11 +396,11 @@ __global__ void rr_adam_step_inc_kernel(float *step) {
   RR_PDL_PROLOGUE();
   step[0] += 1.f;
 }
-static int rrb_adam_step(float *p, const float *g, float *m, float *v, float *step, long long n, float lr, float b1, float b2,
-                         float eps, void *stream) {
+static int rrb_adam_step(float *p, float *g, const float *partials, int nsplit, float *m, float *v, float *step, long long n, float lr,
+                         float b1, float b2, float eps, void *stream) {
   long long blocks = (n + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  if (rrb_check(rr_launch_pdl(rr_adam_kernel, (int)blocks, 256, 0, stream, p, g, m, v, (const float *)step, n, lr, b1, b2, eps), "rr_adam_kernel launch"))
+  if (rrb_check(rr_launch_pdl(rr_adam_kernel, (int)blocks, 256, 0, stream, p, g, partials, nsplit, m, v, (const float *)step, n, lr, b1, b2, eps), "rr_adam_kernel launch"))
     return 1;
   return rrb_check(rr_launch_pdl(rr_adam_step_inc_kernel, 1, 1, 0, stream, step), "rr_adam_step_inc_kernel launch");
 }

@@ -419,7 +419,18 @@ extern "C" int rr_tc_launch(const void *dev_problems, int32_t count, int32_t tot
 extern "C" int rr_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, float *step, int64_t n, float lr,
                             float beta1, float beta2, float eps, void *stream) {
   if (!param || !grad || !exp_avg || !exp_avg_sq || !step || n < 1) return rr_fail(RR_EINVAL, "rr_adam_step: bad argument");
-  if (rrb_adam_step(param, grad, exp_avg, exp_avg_sq, step, n, lr, beta1, beta2, eps, stream)) return rr_fail(RR_ECUDA, rrb_error());
+  if (rrb_adam_step(param, const_cast<float *>(grad), nullptr, 0, exp_avg, exp_avg_sq, step, n, lr, beta1, beta2, eps, stream))
+    return rr_fail(RR_ECUDA, rrb_error());
+  g_rr_launches += 2;
+  return RR_OK;
+}
+
+extern "C" int rr_adam_step_sum(float *param, float *grad, const float *partials, int32_t nsplit, float *exp_avg, float *exp_avg_sq,
+                                float *step, int64_t n, float lr, float beta1, float beta2, float eps, void *stream) {
+  if (!param || !grad || !partials || nsplit < 1 || !exp_avg || !exp_avg_sq || !step || n < 1)
+    return rr_fail(RR_EINVAL, "rr_adam_step_sum: bad argument");
+  if (rrb_adam_step(param, grad, partials, nsplit, exp_avg, exp_avg_sq, step, n, lr, beta1, beta2, eps, stream))
+    return rr_fail(RR_ECUDA, rrb_error());
   g_rr_launches += 2;
   return RR_OK;
 }

@@ -423,9 +423,10 @@ class PPO:
         return total, dict(total_loss=total.detach(), policy_loss=policy_loss.detach(), v_loss=v_loss.detach(),
                            entropy_loss=entropy_loss.detach())
 
-    def loss_and_grads(self, mb: Dict[str, torch.Tensor], zero_grad_to_none: bool = False):
+    def loss_and_grads(self, mb: Dict[str, torch.Tensor], zero_grad_to_none: bool = False, defer_grad_sum: bool = False):
         """Loss of one minibatch and its gradient in every parameter's .grad.  Autograd through cuBLAS, or (cfg.tc_learner) the
-        hand-written forward / backward on the tcgen05 GEMM kernel: 12 grouped launches + the two loss kernels."""
+        hand-written forward / backward on the tcgen05 GEMM kernel: 12 grouped launches + the two loss kernels.  `defer_grad_sum`:
+        the caller steps the optimizer right after (the .grad tensors are complete only after that step)."""
         if not self._use_tc:
             total, metrics = self.loss(mb)
             self.opt.zero_grad(set_to_none=zero_grad_to_none)
@@ -448,7 +449,8 @@ class PPO:
             noise = torch.randn(mb["raw_action"].shape, device=obs.device, generator=self.gen)
         loss_partial, _, _ = launch_ppo_loss(self.env._L, cfg, tc.logits.view(T, b, -1), tc.baseline.view(T, b), tc.bootstrap.view(b),
                                              mb, noise, tc.grad_logits, tc.grad_baseline)
-        tc.backward()
+        # one rank: the optimizer's kernel adds the split weight gradients' partial sums itself (the all-reduce needs them summed)
+        tc.backward(defer_sum_to=self.opt if (defer_grad_sum and self.world == 1) else None)
         return _LazyLossMetrics(loss_partial, T * b, cfg.entropy_cost)
 
     def _allreduce_grads(self):
@@ -526,7 +528,7 @@ class PPO:
             side.wait_stream(torch.cuda.current_stream(self.device))
             with torch.cuda.stream(side):
                 gather()
-                metrics = self.loss_and_grads(st, zero_grad_to_none=True)
+                metrics = self.loss_and_grads(st, zero_grad_to_none=True, defer_grad_sum=True)
                 self._allreduce_grads()
                 self.opt.step()
             torch.cuda.current_stream(self.device).wait_stream(side)
@@ -539,7 +541,7 @@ class PPO:
             in_graph = self.world == 1 or self.cfg.graph_allreduce
             with torch.cuda.graph(g):
                 gather()
-                metrics = self.loss_and_grads(st, zero_grad_to_none=True)
+                metrics = self.loss_and_grads(st, zero_grad_to_none=True, defer_grad_sum=True)
                 if in_graph:
                     self._allreduce_grads()  # NCCL all-reduce of the flat bucket, captured with the rest (no-op on one rank)
                     self.opt.step()
@@ -582,7 +584,7 @@ class PPO:
                     metrics = self._update_graphed(data, idx)
                     continue
                 mb = {k: (v[:, idx] if k != "next_observation_last" else v[idx]) for k, v in data.items()}
-                metrics = self.loss_and_grads(mb)
+                metrics = self.loss_and_grads(mb, defer_grad_sum=True)
                 self._allreduce_grads()
                 self.opt.step()
         if self._use_graph:

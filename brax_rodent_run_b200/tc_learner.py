@@ -44,6 +44,7 @@ class FlatAdam:
 
     def __init__(self, L, flat_param, flat_grad, lr, betas=(0.9, 0.999), eps=1e-8):
         self.L, self.p, self.g, self.lr, self.betas, self.eps = L, flat_param, flat_grad, lr, betas, eps
+        self.partials = None   # [nsplit, n]: when set, the next step() first forms grad = sum of the partials (TcLearner.backward)
         self.state = {0: dict(step=torch.zeros(1, device=flat_param.device), exp_avg=torch.zeros_like(flat_param),
                               exp_avg_sq=torch.zeros_like(flat_param))}
 
@@ -55,6 +56,12 @@ class FlatAdam:
         from . import _lib
         st, c = self.state[0], lambda t: ctypes.c_void_p(t.data_ptr())
         stream = ctypes.c_void_p(torch.cuda.current_stream(self.p.device).cuda_stream) if self.p.is_cuda else None
+        if self.partials is not None:
+            _lib.check(self.L, self.L.rr_adam_step_sum(c(self.p), c(self.g), c(self.partials), self.partials.shape[0], c(st["exp_avg"]),
+                                                       c(st["exp_avg_sq"]), c(st["step"]), self.p.numel(), self.lr, self.betas[0],
+                                                       self.betas[1], self.eps, stream))
+            self.partials = None
+            return
         _lib.check(self.L, self.L.rr_adam_step(c(self.p), c(self.g), c(st["exp_avg"]), c(st["exp_avg_sq"]), c(st["step"]),
                                                self.p.numel(), self.lr, self.betas[0], self.betas[1], self.eps, stream))
 
@@ -180,10 +187,14 @@ class TcLearner:
         for g in self.fwd_groups:
             g.launch()
 
-    def backward(self) -> None:
-        """grad_logits, grad_baseline -> .grad of every weight and bias."""
+    def backward(self, defer_sum_to=None) -> None:
+        """grad_logits, grad_baseline -> .grad of every weight and bias.  `defer_sum_to` (a FlatAdam): leave the sum of the split
+        weight gradients' partials to the optimizer's kernel (one launch less; the .grad tensors are complete after its step())."""
         for g in self.dgrad_groups:
             g.launch()
         self.wgrad_group.launch()
         if self.splits > 1:
-            torch.sum(self.ws, dim=0, out=self.flat_grad)
+            if defer_sum_to is not None:
+                defer_sum_to.partials = self.ws
+            else:
+                torch.sum(self.ws, dim=0, out=self.flat_grad)

@@ -179,6 +179,10 @@ int rr_tc_launch(const void *device_records, int32_t count, int32_t total_tiles,
  * stores step + 1 (capturable in a CUDA graph).  All pointers DEVICE. */
 int rr_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, float *step, int64_t n, float lr, float beta1,
                  float beta2, float eps, void *stream);
+/* The same with the gradient given as `nsplit` partial sums (partials [nsplit, n] contiguous: the split weight-gradient launch's
+ * workspace): grad[i] = sum over s (fixed order) is formed, stored and stepped over in one pass. */
+int rr_adam_step_sum(float *param, float *grad, const float *partials, int32_t nsplit, float *exp_avg, float *exp_avg_sq, float *step,
+                     int64_t n, float lr, float beta1, float beta2, float eps, void *stream);
 
 /* Minibatch gather of the learner: for every item, dst[t, j, :] = src[t, idx[j], :] (src [outer, src_rows, inner] contiguous,
  * dst [outer, rows, inner] with row pitch dst_pitch, fp32); one launch for all items (at most 8).  idx: DEVICE int64 [rows]. */

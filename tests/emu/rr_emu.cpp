@@ -222,10 +222,17 @@ static int rrb_launch_ppo_loss(const RRPpoLossArgs &a, void *) {
 /* Adam and the minibatch gather: the same per-element arithmetic in plain loops */
 #define RR_MISC_HD static inline
 #include "../../brax_rodent_run_b200/csrc/rr_learner_misc.h"
-static int rrb_adam_step(float *p, const float *g, float *m, float *v, float *step, long long n, float lr, float b1, float b2,
-                         float eps, void *) {
+static int rrb_adam_step(float *p, float *g, const float *partials, int nsplit, float *m, float *v, float *step, long long n, float lr,
+                         float b1, float b2, float eps, void *) {
   const float t = step[0] + 1.f;
-  for (long long i = 0; i < n; i++) rr_adam_element(p[i], g[i], m[i], v[i], t, lr, b1, b2, eps);
+  for (long long i = 0; i < n; i++) {
+    if (partials) {
+      float gi = partials[i];
+      for (int s = 1; s < nsplit; s++) gi += partials[(size_t)s * n + i];
+      g[i] = gi;
+    }
+    rr_adam_element(p[i], g[i], m[i], v[i], t, lr, b1, b2, eps);
+  }
   step[0] = t;
   return 0;
 }

@@ -116,10 +116,22 @@ def test_flat_adam_matches_torch_adam(backend, emu_lib):
         g.mul_(0.7).add_(0.1)
     assert float(fa.state[0]["step"]) == 6.0
     assert float((p - ref.data).abs().max()) < 2e-6
+    # the gradient given as partial sums (the split weight-gradient launch's workspace): summed, stored and stepped in one pass
+    parts = torch.randn(4, 70001, generator=g0).to(dev)
+    pc, gc = p.clone(), torch.zeros_like(g)
+    fc = FlatAdam(L, pc, gc, 3e-4)
+    fc.load_state_dict(fa.state_dict())
+    fc.partials = parts
+    fc.step()
+    want_g = ((parts[0] + parts[1]) + parts[2]) + parts[3]
+    assert torch.equal(gc, want_g) and fc.partials is None
+    g.copy_(want_g)
+    fa.step()
+    assert torch.equal(pc, p)
     sd = fa.state_dict()
     fb = FlatAdam(L, p.clone(), g, 3e-4)
     fb.load_state_dict(sd)
-    assert torch.equal(fb.state[0]["exp_avg"], fa.state[0]["exp_avg"]) and float(fb.state[0]["step"]) == 6.0
+    assert torch.equal(fb.state[0]["exp_avg"], fa.state[0]["exp_avg"]) and float(fb.state[0]["step"]) == 7.0
 
 
 @pytest.mark.parametrize("backend", backend_params())
