@@ -65,6 +65,16 @@ class RRGatherItem(ctypes.Structure):
     _fields_ = [("src", vp), ("dst", vp)] + [(n, ctypes.c_int32) for n in ("outer", "src_rows", "inner", "dst_pitch")]
 
 
+RR_POLICY_MAX_LAYERS = 8
+
+
+class RRPolicyArgs(ctypes.Structure):
+    """rr_policy_args (include/rr_b200.h)."""
+    _fields_ = ([(n, vp) for n in ("obs", "mean", "std")] + [("w", vp * RR_POLICY_MAX_LAYERS), ("b", vp * RR_POLICY_MAX_LAYERS)] +
+                [(n, vp) for n in ("eps", "action", "raw_action", "log_prob")] +
+                [(n, ctypes.c_int32) for n in ("B", "obs_dim", "in0", "nlayers", "A")] + [("reserved", ctypes.c_int32 * 3)])
+
+
 _libs = {}
 
 
@@ -112,6 +122,8 @@ def load(path: Optional[str] = None):
     L.rr_adam_step_sum.restype = ctypes.c_int
     L.rr_gather_rows.argtypes = [ctypes.POINTER(RRGatherItem), ctypes.c_int32, vp, ctypes.c_int32, vp]
     L.rr_gather_rows.restype = ctypes.c_int
+    L.rr_policy_act.argtypes = [ctypes.POINTER(RRPolicyArgs), vp]
+    L.rr_policy_act.restype = ctypes.c_int
     L.rr_tc_record_bytes.restype = ctypes.c_int32
     L.rr_tc_plan.argtypes = [ctypes.POINTER(RRTcProblem), ctypes.c_int32, c_i, c_i, vp]
     L.rr_tc_plan.restype = ctypes.c_int

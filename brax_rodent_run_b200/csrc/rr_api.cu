@@ -427,6 +427,98 @@ static int rrb_gather_rows(const RRGatherArgs &a, int blocks, void *stream) {
   return rrb_check(rr_launch_pdl(rr_gather_kernel, blocks, 128, 0, stream, a), "rr_gather_kernel launch");
 }
 
+/* ---- policy inference of the rollout: normalise -> MLP (32-wide swish layers) -> tanh-normal sample + log-prob, one kernel ----
+ * One warp per environment row, lane j = neuron j.  All weights are staged once per (persistent) CTA in shared memory with odd row
+ * pitches, so that "lane j reads column k of its own row" is conflict-free; the input / activations are broadcast by shuffles. */
+#define RR_POLICY_WARPS 8
+__device__ __forceinline__ int rr_policy_pitch0(int obs_dim) { return (((obs_dim + 31) / 32) * 32) | 1; }
+__global__ void __launch_bounds__(32 * RR_POLICY_WARPS, 1) rr_policy_act_kernel(const __grid_constant__ rr_policy_args a) {
+  extern __shared__ float ps[];
+  RR_PDL_PROLOGUE();
+  const int H = RR_POLICY_HIDDEN, P0 = rr_policy_pitch0(a.obs_dim), PH = H + 1, nh = a.nlayers - 2, A = a.A;
+  float *w0 = ps, *wh = w0 + H * P0, *wo = wh + nh * H * PH, *ms = wo + 2 * A * PH, *sd = ms + a.obs_dim;
+  for (int i = threadIdx.x; i < H * P0; i += blockDim.x) {
+    const int j = i / P0, k = i - j * P0;
+    w0[i] = k < a.obs_dim ? a.w[0][(size_t)j * a.in0 + k] : 0.f;
+  }
+  for (int l = 0; l < nh; l++)
+    for (int i = threadIdx.x; i < H * H; i += blockDim.x) wh[l * H * PH + (i / H) * PH + (i % H)] = a.w[1 + l][i];
+  for (int i = threadIdx.x; i < 2 * A * H; i += blockDim.x) wo[(i / H) * PH + (i % H)] = a.w[a.nlayers - 1][i];
+  for (int i = threadIdx.x; i < a.obs_dim; i += blockDim.x) {
+    ms[i] = a.mean ? a.mean[i] : 0.f;
+    sd[i] = a.mean ? a.std[i] : 1.f;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = blockIdx.x * RR_POLICY_WARPS + warp; r < a.B; r += gridDim.x * RR_POLICY_WARPS) {
+    /* layer 0: obs_dim -> 32 */
+    const float *x = a.obs + (size_t)r * a.obs_dim, *wrow = w0 + lane * P0;
+    float acc[4] = {__ldg(a.b[0] + lane), 0.f, 0.f, 0.f};
+    for (int k0 = 0; k0 < a.obs_dim; k0 += 32) {
+      const int k = k0 + lane;
+      float xv = 0.f;
+      if (k < a.obs_dim) xv = (x[k] - ms[k]) / sd[k];
+#pragma unroll
+      for (int kk = 0; kk < 32; kk += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) acc[u] += __shfl_sync(0xffffffffu, xv, kk + u) * wrow[k0 + kk + u];
+      }
+    }
+    float h = rr_policy_silu((acc[0] + acc[1]) + (acc[2] + acc[3]));
+    /* hidden layers 32 -> 32 */
+    for (int l = 0; l < nh; l++) {
+      const float *wr = wh + l * H * PH + lane * PH;
+      float c[4] = {__ldg(a.b[1 + l] + lane), 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int kk = 0; kk < 32; kk += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) c[u] += __shfl_sync(0xffffffffu, h, kk + u) * wr[kk + u];
+      }
+      h = rr_policy_silu((c[0] + c[1]) + (c[2] + c[3]));
+    }
+    /* head 32 -> 2 A: lane k < A forms loc_k and the pre-softplus scale of action k */
+    const bool on = lane < A;
+    const float *wa = wo + (on ? lane : 0) * PH, *wb = wo + (on ? A + lane : 0) * PH;
+    const float *bo = a.b[a.nlayers - 1];
+    float loc = on ? __ldg(bo + lane) : 0.f, pre = on ? __ldg(bo + A + lane) : 0.f;
+#pragma unroll
+    for (int kk = 0; kk < 32; kk++) {
+      const float hv = __shfl_sync(0xffffffffu, h, kk);
+      loc += hv * wa[kk];
+      pre += hv * wb[kk];
+    }
+    float lp = 0.f;
+    if (on) {
+      float act, raw;
+      lp = rr_policy_sample(loc, pre, a.eps ? a.eps + (size_t)r * A + lane : nullptr, act, raw);
+      a.action[(size_t)r * A + lane] = act;
+      a.raw_action[(size_t)r * A + lane] = raw;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lp += __shfl_xor_sync(0xffffffffu, lp, o);
+    if (lane == 0) a.log_prob[r] = lp;
+  }
+}
+static int rrb_policy_act(const rr_policy_args &a, void *stream) {
+  const int H = RR_POLICY_HIDDEN, P0 = (((a.obs_dim + 31) / 32) * 32) | 1;
+  const size_t smem = sizeof(float) * ((size_t)H * P0 + (size_t)(a.nlayers - 2) * H * (H + 1) + (size_t)2 * a.A * (H + 1) + 2 * (size_t)a.obs_dim);
+  if (smem > RR_SMEM_MAX) { snprintf(g_cuda_err, sizeof(g_cuda_err), "rr_policy_act: %zu bytes of weights do not fit shared memory", smem); return 1; }
+  static std::atomic<bool> configured[64];
+  int dev = 0;
+  if (rrb_check(cudaGetDevice(&dev), "cudaGetDevice")) return 1;
+  dev &= 63;
+  if (!configured[dev].load(std::memory_order_acquire)) {
+    if (rrb_check(cudaFuncSetAttribute(rr_policy_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RR_SMEM_MAX), "rr_policy_act attribute"))
+      return 1;
+    configured[dev].store(true, std::memory_order_release);
+  }
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int grid = (a.B + RR_POLICY_WARPS - 1) / RR_POLICY_WARPS;
+  if (grid > sms) grid = sms;
+  return rrb_check(rr_launch_pdl(rr_policy_act_kernel, grid, 32 * RR_POLICY_WARPS, smem, stream, a), "rr_policy_act_kernel launch");
+}
+
 /* grouped TF32 GEMM of the learner on the tensor cores (tcgen05) */
 #define RR_TC_HD __host__ __device__ static inline
 #include "rr_tc_gemm.h"

@@ -456,6 +456,17 @@ extern "C" int rr_gather_rows(const rr_gather_item *items, int32_t count, const 
   return RR_OK;
 }
 
+extern "C" int rr_policy_act(const rr_policy_args *a, void *stream) {
+  if (!a || !a->obs || !a->action || !a->raw_action || !a->log_prob || a->B < 1 || a->obs_dim < 1 || a->in0 < a->obs_dim ||
+      a->nlayers < 2 || a->nlayers > RR_POLICY_MAX_LAYERS || a->A < 1 || a->A > 32 || (a->mean && !a->std))
+    return rr_fail(RR_EINVAL, "rr_policy_act: bad argument (hidden layers are 32 wide, at most 32 actions)");
+  for (int l = 0; l < a->nlayers; l++)
+    if (!a->w[l] || !a->b[l]) return rr_fail(RR_EINVAL, "rr_policy_act: null layer");
+  if (rrb_policy_act(*a, stream)) return rr_fail(RR_ECUDA, rrb_error());
+  g_rr_launches += 1;
+  return RR_OK;
+}
+
 extern "C" int rr_measure_fp32_peak(double *tflops, void *stream) {
   if (!tflops) return rr_fail(RR_EINVAL, "rr_measure_fp32_peak: null argument");
   if (rrb_fp32_peak(tflops, stream)) return rr_fail(RR_ECUDA, rrb_error());

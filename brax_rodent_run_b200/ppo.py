@@ -55,6 +55,9 @@ class PPOConfig:
     tc_learner: Optional[bool] = None  # the two MLPs' forward / backward as 12 grouped TMA + tcgen05 GEMM launches (tc_learner.py),
                                     # Adam and the minibatch gather as own kernels, instead of autograd + cuBLAS (~95 launches);
                                     # needs fused_loss.  None: on for CUDA devices, off on the CPU
+    fused_act: Optional[bool] = None   # rollout policy inference (normalise, MLP, tanh-normal sample, log-prob) as ONE kernel
+                                    # (rr_policy_act) instead of ~20 torch launches per env step; needs 32-wide hidden policy layers
+                                    # and <= 32 actions.  None: on for CUDA devices when the policy fits, off on the CPU
     fused_loss: bool = True         # loss + gradient w.r.t. the network outputs in two hand-written kernels (rr_ppo_loss)
     cuda_graph: bool = True         # replay the minibatch update (loss, backward, Adam) as one CUDA graph on CUDA devices
     graph_allreduce: bool = False   # several ranks: capture the NCCL all-reduce + Adam in the update graph too.  OFF: with torch 2.11 /
@@ -296,6 +299,7 @@ class PPO:
         self.gen.manual_seed(cfg.seed * 1000 + 17 + self.rank)
         self.env_steps = 0
         self._flat_grad = None
+        self._use_fused_act = self._fused_act_ok()
         self._batch_static = None
         self._gather_items = None
 
@@ -309,7 +313,42 @@ class PPO:
         return obs if getattr(self, "_batch_is_normalized", False) else self._norm(obs)
 
     @torch.no_grad()
+    def _fused_act_ok(self) -> bool:
+        lin = [m for m in self.policy if isinstance(m, nn.Linear)]
+        fits = (2 <= len(lin) <= _lib.RR_POLICY_MAX_LAYERS and all(l.out_features == 32 for l in lin[:-1]) and
+                self.env.action_size <= 32 and lin[-1].out_features == 2 * self.env.action_size)
+        want = (self.device.type == "cuda") if self.cfg.fused_act is None else bool(self.cfg.fused_act)
+        if self.cfg.fused_act and not fits:
+            raise ValueError("fused_act needs 32-wide hidden policy layers and at most 32 actions")
+        return want and fits
+
+    def _act_fused(self, obs, deterministic, eps):
+        """rr_policy_act: one kernel from the raw observation to (action, raw action, log-prob)."""
+        B, A = obs.shape[0], self.env.action_size
+        obs = obs.contiguous()
+        if not deterministic and eps is None:
+            eps = torch.randn((B, A), device=obs.device, generator=self.gen)
+        action, raw, lp = (torch.empty((B, A), device=obs.device), torch.empty((B, A), device=obs.device),
+                           torch.empty(B, device=obs.device))
+        lin = [m for m in self.policy if isinstance(m, nn.Linear)]
+        a = _lib.RRPolicyArgs()
+        a.obs = obs.data_ptr()
+        if self.cfg.normalize_observations:
+            a.mean, a.std = self.normalizer.mean.data_ptr(), self.normalizer.std.data_ptr()
+        for i, l in enumerate(lin):
+            a.w[i], a.b[i] = l.weight.data_ptr(), l.bias.data_ptr()
+        a.eps = None if deterministic else eps.contiguous().data_ptr()
+        a.action, a.raw_action, a.log_prob = action.data_ptr(), raw.data_ptr(), lp.data_ptr()
+        a.B, a.obs_dim, a.in0, a.nlayers, a.A = B, self._obs_dim, lin[0].in_features, len(lin), A
+        stream = ctypes.c_void_p(torch.cuda.current_stream(obs.device).cuda_stream) if obs.is_cuda else None
+        _lib.check(self.env._L, self.env._L.rr_policy_act(ctypes.byref(a), stream))
+        if deterministic:
+            lp.zero_()
+        return action, raw, lp
+
     def act(self, obs, deterministic=False, eps=None):
+        if self._use_fused_act:
+            return self._act_fused(obs, deterministic, eps)
         logits = self.policy(self._norm(obs))
         if deterministic:
             loc = logits.chunk(2, dim=-1)[0]

@@ -193,6 +193,20 @@ typedef struct rr_gather_item {
 } rr_gather_item;
 int rr_gather_rows(const rr_gather_item *host_items, int32_t count, const int64_t *idx, int32_t rows, void *stream);
 
+/* Policy inference of the rollout (brax acting.generate_unroll -> policy apply, brax_rodent_run_ppo.py:97-114): observation
+ * normalisation, the policy MLP (hidden layers of width 32, swish) and the tanh-normal sample + log-prob in ONE kernel, fp32.
+ * weights: torch.nn.Linear layout [out, in] row-major (layer 0 with row pitch in0 >= obs_dim: zero-padded input columns are
+ * skipped); eps: standard normal noise [B, A] (null: deterministic, action = tanh(loc), log_prob = 0).  All pointers DEVICE. */
+#define RR_POLICY_MAX_LAYERS 8
+typedef struct rr_policy_args {
+  const float *obs, *mean, *std;                 /* [B, obs_dim], [obs_dim], [obs_dim] (mean null: no normalisation) */
+  const float *w[RR_POLICY_MAX_LAYERS], *b[RR_POLICY_MAX_LAYERS];
+  const float *eps;
+  float *action, *raw_action, *log_prob;         /* [B, A], [B, A], [B] */
+  int32_t B, obs_dim, in0, nlayers, A, reserved[3]; /* nlayers Linear layers: nlayers - 1 hidden (32 wide) + the 2A-wide head */
+} rr_policy_args;
+int rr_policy_act(const rr_policy_args *args, void *stream);
+
 /* Parity-test hooks: per-environment dump of forward-pass intermediates (tests only). */
 int rr_debug_field(const rr_model *m, const char *name, int32_t *offset, int32_t *count);
 int rr_env_set_debug(rr_env *e, float *dbg /* DEVICE [B, debug_stride] or null */);

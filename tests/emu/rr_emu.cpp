@@ -236,6 +236,7 @@ static int rrb_adam_step(float *p, float *g, const float *partials, int nsplit, 
   step[0] = t;
   return 0;
 }
+static int rrb_policy_act(const rr_policy_args &a, void *) { rr_policy_reference(a); return 0; }
 static int rrb_gather_rows(const RRGatherArgs &a, int, void *) {
   for (int it = 0; it < a.count; it++) {
     const rr_gather_item &g = a.item[it];

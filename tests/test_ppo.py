@@ -478,3 +478,41 @@ def test_graphed_tc_update_matches_eager_autograd_update():
     assert float(d_eager.abs().max()) > 0.1 * cfg.learning_rate
     # Adam's normalised step amplifies relative gradient error where the gradient is tiny: compare in the mean
     assert float((d_graph - d_eager).abs().mean()) < 0.05 * float(d_eager.abs().mean())
+
+
+@pytest.mark.parametrize("backend", [pytest.param("emu", id="emu"), pytest.param("cuda", id="cuda", marks=pytest.mark.gpu)])
+def test_fused_act_matches_torch_policy(backend, emu_lib):
+    """rr_policy_act (normalise -> 1263->32x4->60 swish MLP -> tanh-normal sample + log-prob in one kernel) against the torch
+    modules on the same parameters, normaliser and noise; stochastic and deterministic; then a whole unroll with it."""
+    from brax_rodent_run_b200.env import Rodent
+    from brax_rodent_run_b200.ppo import PPO, PPOConfig
+    dev = "cpu" if backend == "emu" else "cuda:0"
+    if backend == "cuda" and not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    n = 5 if backend == "emu" else 300
+    kw = dict(_lib_path=emu_lib) if backend == "emu" else {}
+    env = Rodent(synthetic_track(), num_envs=n, device=dev, model=load_asset("rodent_0"), iterations=1, ls_iterations=1, n_frames=1, **kw)
+    cfg = PPOConfig(num_envs=n, batch_size=n, num_minibatches=1, unroll_length=2, value_hidden=(16,), fused_act=True, tf32=False,
+                    cuda_graph=False, rollout_graph=False)
+    agent = PPO(env.wrap_for_training(20), cfg)
+    assert agent._use_fused_act
+    g = torch.Generator().manual_seed(0)
+    agent.normalizer.mean.copy_(torch.randn(env.observation_size, generator=g))
+    agent.normalizer.std.copy_(torch.rand(env.observation_size, generator=g) + 0.5)
+    obs = (2 * torch.randn(n, env.observation_size, generator=g)).to(dev)
+    eps = torch.randn(n, env.action_size, generator=g).to(dev)
+    if backend == "cuda":
+        torch.backends.cuda.matmul.allow_tf32 = False
+    for deterministic in (False, True):
+        agent._use_fused_act = True
+        fused = agent.act(obs, deterministic, eps)
+        agent._use_fused_act = False
+        ref = agent.act(obs, deterministic, eps)
+        for name, x, y, tol in zip(("action", "raw", "log_prob"), fused, ref, (2e-5, 1e-4, 2e-3)):
+            assert float((x - y).abs().max()) <= tol, (deterministic, name, float((x - y).abs().max()))
+    agent._use_fused_act = True
+    state = env.reset(0) if backend == "cuda" else agent.env.reset(0)
+    state, data = agent.unroll(state)
+    assert torch.isfinite(data["log_prob"]).all() and data["raw_action"].shape == (2, n, env.action_size)
+    with pytest.raises(ValueError):
+        PPO(agent.env, PPOConfig(num_envs=n, batch_size=n, num_minibatches=1, policy_hidden=(8, 8), fused_act=True))
