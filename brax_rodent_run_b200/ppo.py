@@ -312,7 +312,6 @@ class PPO:
         """Observations of a minibatch: already normalised when they come out of training_step's batch."""
         return obs if getattr(self, "_batch_is_normalized", False) else self._norm(obs)
 
-    @torch.no_grad()
     def _fused_act_ok(self) -> bool:
         lin = [m for m in self.policy if isinstance(m, nn.Linear)]
         fits = (2 <= len(lin) <= _lib.RR_POLICY_MAX_LAYERS and all(l.out_features == 32 for l in lin[:-1]) and
@@ -346,6 +345,7 @@ class PPO:
             lp.zero_()
         return action, raw, lp
 
+    @torch.no_grad()
     def act(self, obs, deterministic=False, eps=None):
         if self._use_fused_act:
             return self._act_fused(obs, deterministic, eps)
