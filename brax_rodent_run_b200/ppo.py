@@ -689,10 +689,12 @@ class PPO:
         get = (lambda k: norm.get(k)) if isinstance(norm, dict) else (lambda k: getattr(norm, k, None))
         n = self.normalizer
         as_t = lambda x: torch.as_tensor(np.asarray(x), dtype=torch.float32, device=self.device)
-        n.count = torch.as_tensor(float(np.asarray(get("count"))), dtype=torch.float64, device=self.device)
-        n.mean, n.std = as_t(get("mean")), as_t(get("std"))
+        # in place: the captured rollout graph (and rr_policy_act's argument block) read the normaliser at fixed addresses
+        n.count.copy_(torch.as_tensor(float(np.asarray(get("count"))), dtype=torch.float64, device=self.device))
+        n.mean.copy_(as_t(get("mean")))
+        n.std.copy_(as_t(get("std")))
         sv = get("summed_variance")
-        n.summed_variance = as_t(sv) if sv is not None else (n.std ** 2) * float(n.count)
+        n.summed_variance.copy_(as_t(sv) if sv is not None else (n.std ** 2) * float(n.count))
         layers = pol["params"] if "params" in pol else pol
         lin = [m for m in self.policy if isinstance(m, nn.Linear)]
         if len(layers) != len(lin):
